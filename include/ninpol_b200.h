@@ -1,0 +1,125 @@
+/*
+ * ninpol_b200.h — C ABI of libninpol_b200.so: the sm_100a replacement for ninpol's nodal-interpolation
+ * hot path (Interpolator.load_mesh -> Interpolator.interpolate).
+ *
+ * The reference is a Cython package with no C FFI of its own; the boundary this library replaces is
+ * the set of `cdef` calls its Interpolator makes into Grid and into the IDW / LS / GLS plug-ins.  Each
+ * entry point below names the reference interface it stands in for (paths relative to the reference
+ * repository root).  Conventions:
+ *   - plain C: opaque context pointer, raw host pointers + element counts, no framework types;
+ *   - every function returns 0 on success, non-zero on error; npb_last_error() gives the message of the
+ *     last failure on the calling thread;
+ *   - host arrays are borrowed for the duration of the call only; device state lives in the context;
+ *   - array dtypes/layouts on the host side are the reference's own (int64 ids, -1 padding, float64
+ *     geometry, int32/float64 CSR exactly as scipy returns them), so results compare bit-for-bit;
+ *   - one context drives one GPU on one CUDA stream; multi-GPU = one process (and context) per GPU.
+ * There is no CPU fallback: every call fails with NPB_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef NINPOL_B200_H
+#define NINPOL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NPB_OK 0
+#define NPB_ERR_ARG 1      /* bad argument / unknown name / call order                      */
+#define NPB_ERR_CUDA 2     /* CUDA runtime failure or no usable device                      */
+#define NPB_ERR_NCCL 3     /* NCCL failure or libnccl.so.2 not loadable                     */
+#define NPB_ERR_RANGE 4    /* a count exceeds the 32-bit id range used on the device        */
+#define NPB_ERR_STATE 5    /* e.g. interpolate before load_mesh, missing field              */
+
+#define NPB_METHOD_IDW 0   /* ninpol/_methods/idw.pyx                                        */
+#define NPB_METHOD_LS 1    /* ninpol/_methods/ls.pyx                                         */
+#define NPB_METHOD_GLS 2   /* ninpol/_methods/gls.pyx                                        */
+
+#define NPB_UNIQUE_ID_BYTES 128
+
+typedef struct npb_ctx npb_ctx;
+
+/* library */
+int npb_version(void);
+const char *npb_last_error(void);
+int npb_device_count(int *count);
+
+/* Context: owns one device, one stream, all device arrays.
+ * Replaces: object construction in Interpolator.__cinit__ (ninpol/_interpolator/interpolator.pyx:37-91). */
+int npb_create(int device, npb_ctx **ctx);
+int npb_destroy(npb_ctx *ctx);
+
+/* Multi-GPU wiring (one process per GPU).  Rank 0 calls npb_comm_unique_id and ships the 128 bytes to
+ * the other ranks by any host channel; every rank then calls npb_comm_init.  NCCL is dlopen'ed here, so
+ * single-GPU use needs no NCCL at all.  No reference counterpart (the reference is single-process,
+ * SURVEY.md 2.2). */
+int npb_comm_unique_id(void *id_out /* NPB_UNIQUE_ID_BYTES */);
+int npb_comm_init(npb_ctx *ctx, const void *id, int rank, int world);
+/* node ranges of all ranks: bounds[world+1], bounds[0]=0, bounds[world]=n_points, non-decreasing.
+ * Default (never called, or world==1): this rank owns every node. */
+int npb_set_partition(npb_ctx *ctx, const int64_t *bounds, int n_bounds);
+
+/* K1 — connectivity + geometry on the device.
+ * Replaces: Grid.__cinit__ + Grid.build + load_point_coords + calculate_centroids +
+ * calculate_normal_faces, i.e. the calls at interpolator.pyx:194,204-207 into
+ * ninpol/_interpolator/grid.pyx:47-140,142-231,233-267,304-525,661-809.  Arguments are the tuple
+ * process_mesh returns (interpolator.pyx:363-369) plus the coordinates:
+ *   connectivity  [n_elems, 8]  int64, -1 padded          element_types [n_elems] int64
+ *   npoel[8] nfael[8] lnofa[8][6] lpofa[8][6][4] nedel[8] lpoed[8][12][2]   int64 tables
+ *   coords        [n_points, 3] float64
+ * build_edges != 0 additionally builds inpoed / inedel (grid.pyx:527-580). */
+int npb_load_mesh(npb_ctx *ctx, int dim, int64_t n_elems, int64_t n_points, const int64_t *connectivity,
+                  const int64_t *element_types, const int64_t *npoel, const int64_t *nfael, const int64_t *lnofa,
+                  const int64_t *lpofa, const int64_t *nedel, const int64_t *lpoed, const double *coords,
+                  int build_edges);
+
+/* Grid attributes (grid.pxd:128-187).  Scalars: dim n_elems n_points n_faces n_edges
+ * MX_ELEMENTS_PER_POINT MX_POINTS_PER_POINT MX_ELEMENTS_PER_FACE MX_FACES_PER_POINT, and the flat
+ * lengths len_esup len_fsup len_esuf len_psup.  Arrays (reference dtype and shape, caller-allocated):
+ * inpoel element_types esup esup_ptr psup psup_ptr esuel infael inpofa fsup fsup_ptr esuf esuf_ptr
+ * boundary_faces boundary_points inpoed inedel (int64);  point_coords centroids faces_centers
+ * normal_faces faces_areas (float64). */
+int npb_grid_scalar(npb_ctx *ctx, const char *name, int64_t *out);
+int npb_grid_array(npb_ctx *ctx, const char *name, void *out, int64_t capacity_bytes);
+
+/* Per-variable inputs of the plug-ins.
+ * Replaces: the cells_data / points_data rows the plug-ins look up through variable_to_index
+ * (idw.pyx:27-28, ls.pyx:28-29, gls.pyx:47-59).  name is "permeability" (n = 9*n_elems, row-major 3x3
+ * per element) or "diff_mag" (n = n_elems).  neumann_flag holds int64 truncations of the point data
+ * (non-zero = Neumann node), exactly what `.astype(int)` yields in the reference. */
+int npb_set_cell_field(npb_ctx *ctx, const char *name, const double *data, int64_t n);
+int npb_set_point_flags(npb_ctx *ctx, const int64_t *neumann_flag, int64_t n_points);
+
+/* K2 + K3 (+ K4) — weights and CSR.
+ * Replaces: Interpolator.prepare_interpolator -> XInterpolation.prepare (interpolator.pyx:631-670;
+ * idw.pyx:14-84, ls.pyx:21-135, gls.pyx:38-474) and the COO fill / COO->CSR / eliminate_zeros of
+ * Interpolator.interpolate (interpolator.pyx:598-624), for target_points = all nodes.
+ * npb_interpolate_count runs the weight kernels for this rank's node range, counts the surviving
+ * entries per row, (multi-GPU: all-gathers the row counts), scans them into indptr and reports the
+ * global nnz.  npb_interpolate_fetch fills indices/data/neumann at their global offsets, (multi-GPU:
+ * all-gathers the row blocks over NCCL) and copies the full CSR + neumann vector into caller memory:
+ *   indptr [n_points+1] int32, indices [nnz] int32, data [nnz] float64, neumann [n_points] float64.
+ * Any output pointer may be NULL to skip that copy. */
+int npb_interpolate_count(npb_ctx *ctx, int method, int64_t *nnz);
+int npb_interpolate_fetch(npb_ctx *ctx, int32_t *indptr, int32_t *indices, double *data, double *neumann);
+
+/* Device-side timings (CUDA events on the context's stream) of the most recent calls, in ms.
+ * Names: "k1" "k1_esup" "k1_esuel" "k1_faces" "k1_fsup" "k1_geom" "k2" "k3_count" "k3_fill" "k4_gather"
+ * "h2d_mesh" "d2h_csr".  Replaces the clock_gettime stopwatches of grid.pyx:150-227 /
+ * interpolator.pyx:608-668. */
+int npb_timing(npb_ctx *ctx, const char *name, double *ms);
+/* Number of this library's kernel launches since the context was created (bench.py's gpu_launches). */
+int npb_launch_count(npb_ctx *ctx, int64_t *count);
+
+/* Measurement helpers used by bench.py for the roofline denominators that MEASURED_PEAKS.json lacks:
+ * a register-resident DFMA loop (FP64 TFLOP/s) and a device copy (GB/s, read+write). */
+int npb_measure_fp64_peak(npb_ctx *ctx, double *tflops);
+int npb_measure_copy_bw(npb_ctx *ctx, int64_t bytes, double *gbs);
+/* Writes `bytes` of device memory (an L2 flush between timed iterations). */
+int npb_flush_l2(npb_ctx *ctx, int64_t bytes);
+int npb_synchronize(npb_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NINPOL_B200_H */

@@ -1,0 +1,185 @@
+"""ctypes binding of libninpol_b200.so (include/ninpol_b200.h).
+
+This is the only way the Python host reaches the device; there is no PyTorch, no Triton and no CPU
+fallback behind it: if the shared library is missing or no sm_100 GPU is usable, calls raise.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libninpol_b200.so")
+
+METHOD_IDS = {"idw": 0, "ls": 1, "gls": 2}
+UNIQUE_ID_BYTES = 128
+
+_c_i64p = ctypes.POINTER(ctypes.c_int64)
+_SIGNATURES = {
+    "npb_version": (ctypes.c_int, []),
+    "npb_last_error": (ctypes.c_char_p, []),
+    "npb_device_count": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    "npb_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    "npb_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "npb_comm_unique_id": (ctypes.c_int, [ctypes.c_void_p]),
+    "npb_comm_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
+    "npb_set_partition": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "npb_load_mesh": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64] + [ctypes.c_void_p] * 9 + [ctypes.c_int]),
+    "npb_grid_scalar": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, _c_i64p]),
+    "npb_grid_array": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64]),
+    "npb_set_cell_field": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64]),
+    "npb_set_point_flags": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]),
+    "npb_interpolate_count": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_i64p]),
+    "npb_interpolate_fetch": (ctypes.c_int, [ctypes.c_void_p] * 5),
+    "npb_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]),
+    "npb_launch_count": (ctypes.c_int, [ctypes.c_void_p, _c_i64p]),
+    "npb_measure_fp64_peak": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),
+    "npb_measure_copy_bw": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_double)]),
+    "npb_flush_l2": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64]),
+    "npb_synchronize": (ctypes.c_int, [ctypes.c_void_p]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+class NinpolB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree shared library; fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NinpolB200Error(
+                f"{LIB_PATH} not found: build it with `python -m ninpol_b200.build` (nvcc, sm_100a). "
+                "ninpol_b200 has no CPU fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+def check(rc):
+    if rc != 0:
+        msg = load_library().npb_last_error().decode("utf-8", "replace")
+        raise NinpolB200Error(f"libninpol_b200 error {rc}: {msg}")
+
+
+def device_count():
+    n = ctypes.c_int(0)
+    check(load_library().npb_device_count(ctypes.byref(n)))
+    return n.value
+
+
+def comm_unique_id():
+    buf = ctypes.create_string_buffer(UNIQUE_ID_BYTES)
+    check(load_library().npb_comm_unique_id(buf))
+    return buf.raw
+
+
+class Context:
+    """One device context (one GPU, one stream)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self.handle = ctypes.c_void_p()
+        check(self.lib.npb_create(int(device), ctypes.byref(self.handle)))
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self.lib.npb_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- multi-GPU ---
+    def comm_init(self, unique_id, rank, world):
+        buf = ctypes.create_string_buffer(bytes(unique_id), UNIQUE_ID_BYTES)
+        check(self.lib.npb_comm_init(self.handle, buf, int(rank), int(world)))
+
+    def set_partition(self, bounds):
+        b = np.ascontiguousarray(bounds, dtype=np.int64)
+        check(self.lib.npb_set_partition(self.handle, _ptr(b), len(b)))
+
+    # --- K1 ---
+    def load_mesh(self, dim, n_elems, n_points, conn, etype, npoel, nfael, lnofa, lpofa, nedel, lpoed, coords, build_edges):
+        arrs = [np.ascontiguousarray(a, dtype=np.int64) for a in (conn, etype, npoel, nfael, lnofa, lpofa, nedel, lpoed)]
+        coords = np.ascontiguousarray(coords, dtype=np.float64)
+        assert arrs[0].shape == (n_elems, 8) and coords.shape == (n_points, 3)
+        check(self.lib.npb_load_mesh(self.handle, int(dim), int(n_elems), int(n_points), *[_ptr(a) for a in arrs],
+                                     _ptr(coords), int(bool(build_edges))))
+
+    def scalar(self, name):
+        v = ctypes.c_int64(0)
+        check(self.lib.npb_grid_scalar(self.handle, name.encode(), ctypes.byref(v)))
+        return int(v.value)
+
+    def array(self, name, shape, dtype):
+        out = np.empty(shape, dtype=dtype)
+        check(self.lib.npb_grid_array(self.handle, name.encode(), _ptr(out), out.nbytes))
+        return out
+
+    # --- per-variable inputs ---
+    def set_cell_field(self, name, data):
+        d = np.ascontiguousarray(data, dtype=np.float64).ravel()
+        check(self.lib.npb_set_cell_field(self.handle, name.encode(), _ptr(d), d.size))
+
+    def set_point_flags(self, flags):
+        f = np.ascontiguousarray(flags, dtype=np.int64)
+        check(self.lib.npb_set_point_flags(self.handle, _ptr(f), f.size))
+
+    # --- K2 / K3 / K4 ---
+    def interpolate_count(self, method):
+        nnz = ctypes.c_int64(0)
+        check(self.lib.npb_interpolate_count(self.handle, METHOD_IDS[method], ctypes.byref(nnz)))
+        return int(nnz.value)
+
+    def interpolate_fetch(self, indptr, indices, data, neumann):
+        check(self.lib.npb_interpolate_fetch(self.handle, _ptr(indptr), _ptr(indices), _ptr(data), _ptr(neumann)))
+
+    # --- measurement ---
+    def timing(self, name):
+        v = ctypes.c_double(0.0)
+        check(self.lib.npb_timing(self.handle, name.encode(), ctypes.byref(v)))
+        return float(v.value)
+
+    def timing_or(self, name, default=0.0):
+        v = ctypes.c_double(0.0)
+        rc = self.lib.npb_timing(self.handle, name.encode(), ctypes.byref(v))
+        return float(v.value) if rc == 0 else default
+
+    def launch_count(self):
+        v = ctypes.c_int64(0)
+        check(self.lib.npb_launch_count(self.handle, ctypes.byref(v)))
+        return int(v.value)
+
+    def measure_fp64_peak(self):
+        v = ctypes.c_double(0.0)
+        check(self.lib.npb_measure_fp64_peak(self.handle, ctypes.byref(v)))
+        return float(v.value)
+
+    def measure_copy_bw(self, nbytes=1 << 31):
+        v = ctypes.c_double(0.0)
+        check(self.lib.npb_measure_copy_bw(self.handle, int(nbytes), ctypes.byref(v)))
+        return float(v.value)
+
+    def flush_l2(self, nbytes=256 << 20):
+        check(self.lib.npb_flush_l2(self.handle, int(nbytes)))
+
+    def synchronize(self):
+        check(self.lib.npb_synchronize(self.handle))

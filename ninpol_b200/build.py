@@ -1,0 +1,69 @@
+"""Build recipe for libninpol_b200.so: explicit nvcc for sm_100a, in-tree output (the .so is
+git-ignored but travels to the GPU box with the gpurun snapshot).
+
+    python -m ninpol_b200.build [--force]
+
+Bit-exact translation units (geometry, IDW/LS) are compiled with -fmad=false on top of their explicit
+_rn intrinsics; everything carries -lineinfo so ncu's source page maps to the .cu files.
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "_obj")
+LIB = os.path.join(HERE, "libninpol_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-ccbin", "/usr/bin/g++"]
+UNITS = {
+    "capi.cu": [],
+    "scan.cu": [],
+    "export.cu": [],
+    "k1_connectivity.cu": [],
+    "k1_geometry.cu": ["-fmad=false"],
+    "k2_idw_ls.cu": ["-fmad=false"],
+    "k2_gls.cu": [],
+    "k3_emit.cu": [],
+    "k4_shard.cu": [],
+}
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OBJ, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(HERE, "..", "include", "ninpol_b200.h"))
+    jobs = []
+    objs = []
+    for src, extra in UNITS.items():
+        s = os.path.join(CSRC, src)
+        o = os.path.join(OBJ, src.replace(".cu", ".o"))
+        objs.append(o)
+        if force or _stale(o, [s] + headers):
+            jobs.append([NVCC] + ARCH + COMMON + extra + ["-c", s, "-o", o])
+
+    def run(cmd):
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if verbose or r.returncode != 0:
+            sys.stderr.write(" ".join(cmd) + "\n" + r.stdout)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed for " + cmd[-3])
+
+    with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
+        list(ex.map(run, jobs))
+    if jobs or force or _stale(LIB, objs):
+        run([NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-ldl", "-ccbin", "/usr/bin/g++"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

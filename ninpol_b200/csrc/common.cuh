@@ -1,0 +1,146 @@
+// common.cuh — context, device-buffer bookkeeping and element tables shared by the translation units
+// of libninpol_b200.so.  Device ids are int32 (every count the reference can index is < 2^31,
+// SURVEY.md App. A.9), geometry is float64.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <map>
+#include <string>
+#include <vector>
+#include "../../include/ninpol_b200.h"
+
+typedef long long i64;
+
+#define NPB_MX_PE 8
+#define NPB_MX_FE 6
+#define NPB_MX_PF 4
+#define NPB_N_TYPES 8
+#define NPB_MX_EE 12
+
+// element tables (reference utils/point_ordering.yaml via process_mesh, interpolator.pyx:274-330);
+// passed to kernels by value -> lives in the constant bank.
+struct ElemTables {
+    int8_t npoel[NPB_N_TYPES];
+    int8_t nfael[NPB_N_TYPES];
+    int8_t lnofa[NPB_N_TYPES][NPB_MX_FE];
+    int8_t lpofa[NPB_N_TYPES][NPB_MX_FE][NPB_MX_PF];
+};
+struct EdgeTables {
+    int8_t nedel[NPB_N_TYPES];
+    int8_t lpoed[NPB_N_TYPES][NPB_MX_EE][2];
+};
+
+void npb_set_error(const char *fmt, ...);
+
+#define NPB_CUDA(call)                                                                            \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            npb_set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e__), __FILE__, __LINE__, #call); \
+            return NPB_ERR_CUDA;                                                                  \
+        }                                                                                         \
+    } while (0)
+
+#define NPB_TRY(call)                \
+    do {                             \
+        int r__ = (call);            \
+        if (r__ != NPB_OK) return r__; \
+    } while (0)
+
+struct NcclApi;  // k4_shard.cu
+
+struct npb_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    i64 launches = 0;
+    std::map<std::string, float> timings;
+    std::vector<void *> owned;  // everything cudaMalloc'ed for the current mesh
+
+    // ---- mesh (K1 outputs) ----
+    bool mesh_loaded = false;
+    int dim = 0;
+    i64 n_elems = 0, n_points = 0, n_faces = 0, n_edges = 0;
+    int spe = 8;  // row stride of inpoel on the device (4 for pure-tet/quad/tri meshes, else 8)
+    int sfe = 6;  // row stride of esuel / infael on the device (4 or 6)
+    i64 len_esup = 0, len_fsup = 0, len_esuf = 0, len_psup = 0;
+    int mx_epp = 0, mx_fpp = 0, mx_epf = 0, mx_ppp = 0;
+    ElemTables tab;
+    EdgeTables etab;
+    bool build_edges = false;
+    int32_t *inpoel = nullptr;   // [n_elems, spe], -1 padded
+    uint8_t *etype = nullptr;    // [n_elems]
+    double *coords = nullptr;    // [n_points, 3]
+    int32_t *esup_ptr = nullptr, *esup = nullptr;
+    int32_t *esuel = nullptr, *infael = nullptr;  // [n_elems, sfe]
+    int32_t *inpofa = nullptr;   // [n_faces, 4], -1 padded
+    int2 *esuf2 = nullptr;       // [n_faces] (owner, other | -1)
+    uint8_t *bface = nullptr, *bpoint = nullptr;
+    int32_t *fsup_ptr = nullptr, *fsup = nullptr;
+    int32_t *psup_ptr = nullptr, *psup = nullptr;
+    int32_t *inedel = nullptr, *inpoed = nullptr;
+    double *centroids = nullptr, *fcent = nullptr, *fnormal = nullptr, *farea = nullptr;
+
+    // ---- per-variable inputs ----
+    double *perm = nullptr, *diff_mag = nullptr;
+    uint8_t *nflag = nullptr;
+    bool have_perm = false, have_dm = false, have_flags = false;
+
+    // ---- partition / communicator ----
+    int rank = 0, world = 1;
+    std::vector<i64> bounds;  // world+1
+    i64 lo = 0, hi = 0;       // this rank's node range
+    i64 wbase = 0;            // esup_ptr[lo]: origin of wbuf
+    i64 wlen = 0;             // esup_ptr[hi] - esup_ptr[lo]
+    NcclApi *nccl = nullptr;
+    void *comm = nullptr;
+
+    // ---- interpolate state ----
+    int method = -1;
+    bool counted = false;
+    i64 nnz = 0;
+    double *wbuf = nullptr;      // final data values, esup-indexed, local node range
+    size_t wbuf_cap = 0;
+    int32_t *rowcnt = nullptr;   // [n_points + 1]
+    int32_t *indptr = nullptr;   // [n_points + 1]
+    double *neumann = nullptr;   // [n_points]
+    int32_t *indices = nullptr;
+    double *data = nullptr;
+    size_t out_cap = 0;
+    void *scratch = nullptr;     // scan / select temp storage
+    size_t scratch_cap = 0;
+    int32_t *node_list = nullptr;  // GLS work lists
+    void *gls_ws = nullptr;
+    size_t gls_ws_cap = 0;
+    int *counters = nullptr;     // small device int array (work counters, flags)
+};
+
+// ---- helpers implemented in capi.cu ----
+int npb_alloc(npb_ctx *c, void **p, size_t bytes, bool owned_by_mesh = true);
+int npb_ensure(void **p, size_t *cap, size_t bytes);
+struct NpbTimer {
+    npb_ctx *c;
+    const char *name;
+    cudaEvent_t a, b;
+    NpbTimer(npb_ctx *c_, const char *n);
+    void stop();
+};
+
+// ---- scan.cu (CUB) ----
+int npb_exclusive_scan_i32(npb_ctx *c, const int32_t *in, int32_t *out, i64 n);   // out may alias in
+int npb_max_i32(npb_ctx *c, const int32_t *in, i64 n, int32_t *host_out);
+int npb_select_class(npb_ctx *c, const uint8_t *cls, i64 lo, i64 hi, int which, int32_t *out, int *host_count);
+
+// ---- kernels' host drivers ----
+int npb_k1_build(npb_ctx *c, const i64 *h_conn, const i64 *h_types, const double *h_coords);
+int npb_k1_geometry(npb_ctx *c);
+int npb_k1_extras(npb_ctx *c);  // psup, edges
+int npb_k2_idw_ls(npb_ctx *c, int method, i64 lo, i64 hi);
+int npb_k2_gls(npb_ctx *c, i64 lo, i64 hi);
+int npb_k3_fill(npb_ctx *c, i64 lo, i64 hi);
+int npb_k4_gather_counts(npb_ctx *c);
+int npb_k4_gather_blocks(npb_ctx *c);
+int npb_export_array(npb_ctx *c, const char *name, void *out, i64 cap);
+
+static inline unsigned npb_blocks(i64 n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+#define NPB_LAUNCH(c) ((c)->launches++)

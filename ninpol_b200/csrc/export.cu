@@ -1,0 +1,215 @@
+// export.cu — Grid attribute export in the reference's dtypes and shapes (grid.pxd:128-187), plus the
+// structures no interpolation method consumes and that are therefore built lazily: psup
+// (Grid.build_psup, ninpol/_interpolator/grid.pyx:269-302).  Device arrays are int32 / compact; the
+// widening to int64, the -1 padding to [n,8] / [n,6] / [n,4] and the (ptr, flat) form of esuf are done
+// by kernels here, then copied to caller memory.
+#include <string.h>
+#include "common.cuh"
+
+__global__ void k_widen_rows(const int32_t *__restrict__ src, i64 rows, int src_stride, int dst_stride, i64 *__restrict__ dst)
+{
+    i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * dst_stride) return;
+    i64 r = idx / dst_stride;
+    int j = (int)(idx - r * dst_stride);
+    dst[idx] = j < src_stride ? (i64)src[r * src_stride + j] : -1;
+}
+__global__ void k_widen_u8(const uint8_t *__restrict__ src, i64 n, i64 *__restrict__ dst)
+{
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+__global__ void k_esuf_count(const int2 *__restrict__ esuf2, i64 n_faces, int32_t *__restrict__ cnt)
+{
+    i64 f = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f > n_faces) return;
+    cnt[f] = f == n_faces ? 0 : (esuf2[f].y >= 0 ? 2 : 1);
+}
+__global__ void k_esuf_flat(const int2 *__restrict__ esuf2, const int32_t *__restrict__ ptr, i64 n_faces, i64 *__restrict__ out)
+{
+    i64 f = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_faces) return;
+    int2 e = esuf2[f];
+    out[ptr[f]] = e.x;
+    if (e.y >= 0) out[ptr[f] + 1] = e.y;
+}
+
+// ---- psup: first-occurrence order over (esup row, local node), grid.pyx:285-299 ----
+#define PSUP_CAP 256
+template <bool FILL>
+__global__ void k_psup(ElemTables tab, const int32_t *__restrict__ inpoel, const uint8_t *__restrict__ etype,
+                       const int32_t *__restrict__ esup_ptr, const int32_t *__restrict__ esup, i64 n_points, int spe,
+                       int32_t *__restrict__ cnt_or_ptr, int32_t *__restrict__ psup, int *__restrict__ flags)
+{
+    i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p > n_points) return;
+    if (p == n_points) {
+        if (!FILL) cnt_or_ptr[p] = 0;
+        return;
+    }
+    int seen[PSUP_CAP];
+    int n = 0;
+    for (int q = esup_ptr[p]; q < esup_ptr[p + 1]; q++) {
+        int e = esup[q];
+        int npe = tab.npoel[etype[e]];
+        for (int k = 0; k < npe; k++) {
+            int v = inpoel[(i64)e * spe + k];
+            if (v == (int)p) continue;
+            bool dup = false;
+            for (int s = 0; s < n; s++) dup = dup || (seen[s] == v);
+            if (dup) continue;
+            if (n < PSUP_CAP) seen[n] = v;
+            else atomicExch(&flags[0], 1);
+            n++;
+        }
+    }
+    if (FILL) {
+        int b = cnt_or_ptr[p];
+        for (int s = 0; s < n && s < PSUP_CAP; s++) psup[b + s] = seen[s];
+    } else {
+        cnt_or_ptr[p] = n;
+        atomicMax(&flags[1], n);
+    }
+}
+
+static int build_psup(npb_ctx *c)
+{
+    if (c->psup_ptr) return NPB_OK;
+    cudaStream_t s = c->stream;
+    i64 np = c->n_points;
+    int *flags = c->counters + 32;
+    NPB_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 2, s));
+    int32_t *ptr = nullptr;
+    NPB_TRY(npb_alloc(c, (void **)&ptr, sizeof(int32_t) * (np + 1)));
+    k_psup<false><<<npb_blocks(np + 1, 128), 128, 0, s>>>(c->tab, c->inpoel, c->etype, c->esup_ptr, c->esup, np, c->spe, ptr,
+                                                         nullptr, flags);
+    NPB_LAUNCH(c);
+    int h[2] = {0, 0};
+    NPB_CUDA(cudaMemcpyAsync(h, flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
+    NPB_CUDA(cudaStreamSynchronize(s));
+    if (h[0]) {
+        npb_set_error("psup: a node has more than %d neighbours", PSUP_CAP);
+        return NPB_ERR_RANGE;
+    }
+    c->mx_ppp = h[1];
+    NPB_TRY(npb_exclusive_scan_i32(c, ptr, ptr, np + 1));
+    int32_t total = 0;
+    NPB_CUDA(cudaMemcpyAsync(&total, ptr + np, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    NPB_CUDA(cudaStreamSynchronize(s));
+    c->len_psup = total;
+    NPB_TRY(npb_alloc(c, (void **)&c->psup, sizeof(int32_t) * (size_t)(total > 0 ? total : 1)));
+    k_psup<true><<<npb_blocks(np + 1, 128), 128, 0, s>>>(c->tab, c->inpoel, c->etype, c->esup_ptr, c->esup, np, c->spe, ptr,
+                                                        c->psup, flags);
+    NPB_LAUNCH(c);
+    c->psup_ptr = ptr;
+    return NPB_OK;
+}
+
+int npb_k1_extras(npb_ctx *c)
+{
+    // psup is built on first use (npb_export_array / npb_psup_stats); edges: see DESIGN.md, "next" row
+    (void)c;
+    return NPB_OK;
+}
+
+int npb_psup_stats(npb_ctx *c)
+{
+    return build_psup(c);
+}
+
+static int out_i64(npb_ctx *c, const i64 *dev, i64 n, void *out, i64 cap)
+{
+    if (cap < (i64)sizeof(i64) * n) {
+        npb_set_error("output buffer too small: need %lld bytes, have %lld", (long long)(sizeof(i64) * n), (long long)cap);
+        return NPB_ERR_ARG;
+    }
+    if (n > 0) NPB_CUDA(cudaMemcpyAsync(out, dev, sizeof(i64) * n, cudaMemcpyDeviceToHost, c->stream));
+    NPB_CUDA(cudaStreamSynchronize(c->stream));
+    return NPB_OK;
+}
+
+static int export_rows(npb_ctx *c, const int32_t *src, i64 rows, int ss, int ds, void *out, i64 cap)
+{
+    i64 n = rows * ds;
+    i64 *tmp = nullptr;
+    NPB_CUDA(cudaMalloc(&tmp, sizeof(i64) * (size_t)(n > 0 ? n : 1)));
+    if (n > 0) {
+        k_widen_rows<<<npb_blocks(n, 256), 256, 0, c->stream>>>(src, rows, ss, ds, tmp);
+        NPB_LAUNCH(c);
+    }
+    int rc = out_i64(c, tmp, n, out, cap);
+    cudaFree(tmp);
+    return rc;
+}
+
+static int export_f64(npb_ctx *c, const double *src, i64 n, void *out, i64 cap)
+{
+    if (cap < (i64)sizeof(double) * n) {
+        npb_set_error("output buffer too small: need %lld bytes, have %lld", (long long)(sizeof(double) * n), (long long)cap);
+        return NPB_ERR_ARG;
+    }
+    if (n > 0) NPB_CUDA(cudaMemcpyAsync(out, src, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    NPB_CUDA(cudaStreamSynchronize(c->stream));
+    return NPB_OK;
+}
+
+int npb_export_array(npb_ctx *c, const char *name, void *out, i64 cap)
+{
+    i64 ne = c->n_elems, np = c->n_points, nf = c->n_faces;
+    if (!strcmp(name, "point_coords")) return export_f64(c, c->coords, np * 3, out, cap);
+    if (!strcmp(name, "centroids")) return export_f64(c, c->centroids, ne * 3, out, cap);
+    if (!strcmp(name, "faces_centers")) return export_f64(c, c->fcent, nf * 3, out, cap);
+    if (!strcmp(name, "normal_faces")) return export_f64(c, c->fnormal, nf * 3, out, cap);
+    if (!strcmp(name, "faces_areas")) return export_f64(c, c->farea, nf, out, cap);
+    if (!strcmp(name, "inpoel")) return export_rows(c, c->inpoel, ne, c->spe, NPB_MX_PE, out, cap);
+    if (!strcmp(name, "esuel")) return export_rows(c, c->esuel, ne, c->sfe, NPB_MX_FE, out, cap);
+    if (!strcmp(name, "infael")) return export_rows(c, c->infael, ne, c->sfe, NPB_MX_FE, out, cap);
+    if (!strcmp(name, "inpofa")) return export_rows(c, c->inpofa, nf, NPB_MX_PF, NPB_MX_PF, out, cap);
+    if (!strcmp(name, "esup")) return export_rows(c, c->esup, c->len_esup, 1, 1, out, cap);
+    if (!strcmp(name, "esup_ptr")) return export_rows(c, c->esup_ptr, np + 1, 1, 1, out, cap);
+    if (!strcmp(name, "fsup")) return export_rows(c, c->fsup, c->len_fsup, 1, 1, out, cap);
+    if (!strcmp(name, "fsup_ptr")) return export_rows(c, c->fsup_ptr, np + 1, 1, 1, out, cap);
+    if (!strcmp(name, "psup") || !strcmp(name, "psup_ptr")) {
+        NPB_TRY(build_psup(c));
+        if (!strcmp(name, "psup")) return export_rows(c, c->psup, c->len_psup, 1, 1, out, cap);
+        return export_rows(c, c->psup_ptr, np + 1, 1, 1, out, cap);
+    }
+    if (!strcmp(name, "element_types") || !strcmp(name, "boundary_faces") || !strcmp(name, "boundary_points")) {
+        const uint8_t *src = !strcmp(name, "element_types") ? c->etype : (!strcmp(name, "boundary_faces") ? c->bface : c->bpoint);
+        i64 n = !strcmp(name, "element_types") ? ne : (!strcmp(name, "boundary_faces") ? nf : np);
+        i64 *tmp = nullptr;
+        NPB_CUDA(cudaMalloc(&tmp, sizeof(i64) * (size_t)(n > 0 ? n : 1)));
+        if (n > 0) {
+            k_widen_u8<<<npb_blocks(n, 256), 256, 0, c->stream>>>(src, n, tmp);
+            NPB_LAUNCH(c);
+        }
+        int rc = out_i64(c, tmp, n, out, cap);
+        cudaFree(tmp);
+        return rc;
+    }
+    if (!strcmp(name, "esuf") || !strcmp(name, "esuf_ptr")) {
+        int32_t *ptr = nullptr;
+        NPB_CUDA(cudaMalloc(&ptr, sizeof(int32_t) * (size_t)(nf + 1)));
+        k_esuf_count<<<npb_blocks(nf + 1, 256), 256, 0, c->stream>>>(c->esuf2, nf, ptr);
+        NPB_LAUNCH(c);
+        int rc = npb_exclusive_scan_i32(c, ptr, ptr, nf + 1);
+        if (rc == NPB_OK) {
+            if (!strcmp(name, "esuf_ptr")) {
+                rc = export_rows(c, ptr, nf + 1, 1, 1, out, cap);
+            } else {
+                i64 *tmp = nullptr;
+                NPB_CUDA(cudaMalloc(&tmp, sizeof(i64) * (size_t)(c->len_esuf > 0 ? c->len_esuf : 1)));
+                if (nf > 0) {
+                    k_esuf_flat<<<npb_blocks(nf, 256), 256, 0, c->stream>>>(c->esuf2, ptr, nf, tmp);
+                    NPB_LAUNCH(c);
+                }
+                rc = out_i64(c, tmp, c->len_esuf, out, cap);
+                cudaFree(tmp);
+            }
+        }
+        cudaFree(ptr);
+        return rc;
+    }
+    npb_set_error("npb_grid_array: unknown or unavailable array '%s'", name);
+    return NPB_ERR_ARG;
+}

@@ -1,0 +1,344 @@
+// k1_connectivity.cu — load_mesh connectivity on the device (kernel group K1, integer part).
+//
+// Replaces the serial / OpenMP loops of the reference's Grid.build (ninpol/_interpolator/grid.pyx):
+//   build_esup  :233-267   node -> element CSR      = histogram + exclusive scan + fill + per-row sort
+//   build_esuel :449-525   element -> element       = one thread per (element, local face)
+//   build_infael:304-345   global face numbering    = exclusive scan of ownership flags
+//   build_fsup  :347-379   node -> face CSR         = histogram + scan + fill + per-row sort
+//   build_esuf  :381-444   face -> elements + boundary face / node tags
+// All outputs are bit-identical to the reference's (rows ascending, first-encounter face numbering);
+// the equivalences are spelled out in SURVEY.md App. A and checked in tests/test_gpu_parity.py.
+// Everything here is HBM-bound integer work: ids are int32 on the device, rows are compact.
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// int64 [n_elems, 8] (-1 padded) host layout  ->  int32 [n_elems, spe] + uint8 element types
+// ------------------------------------------------------------------------------------------------
+__global__ void k_convert_conn(const i64 *__restrict__ conn, const i64 *__restrict__ types, i64 n_elems, int spe,
+                               int32_t *__restrict__ inpoel, uint8_t *__restrict__ etype)
+{
+    i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_elems * spe) return;
+    i64 e = idx / spe;
+    int j = (int)(idx - e * spe);
+    inpoel[idx] = (int32_t)conn[e * NPB_MX_PE + j];
+    if (j == 0) etype[e] = (uint8_t)types[e];
+}
+
+// histogram of node incidences over the padded (element, local node) table
+__global__ void k_count_nodes(const int32_t *__restrict__ table, i64 n, int32_t *__restrict__ cnt)
+{
+    i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    int p = table[idx];
+    if (p >= 0) atomicAdd(&cnt[p], 1);
+}
+
+// scatter owner ids into the rows (arbitrary order inside a row; k_sort_rows restores ascending order)
+__global__ void k_fill_rows(const int32_t *__restrict__ table, i64 n, int stride, const int32_t *__restrict__ ptr,
+                            int32_t *__restrict__ cursor, int32_t *__restrict__ out)
+{
+    i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    int p = table[idx];
+    if (p < 0) return;
+    int pos = atomicAdd(&cursor[p], 1);
+    out[(i64)ptr[p] + pos] = (int32_t)(idx / stride);
+}
+
+// ascending insertion sort of every CSR row (rows are short: <= MX_*_PER_POINT) + row-length maximum
+__global__ void k_sort_rows(const int32_t *__restrict__ ptr, i64 n_rows, int32_t *__restrict__ vals, int *__restrict__ mx)
+{
+    i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    int len = 0;
+    if (r < n_rows) {
+        i64 b = ptr[r];
+        len = ptr[r + 1] - ptr[r];
+        int32_t *row = vals + b;
+        for (int i = 1; i < len; i++) {
+            int32_t v = row[i];
+            int j = i - 1;
+            while (j >= 0 && row[j] > v) {
+                row[j + 1] = row[j];
+                j--;
+            }
+            row[j + 1] = v;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+    if ((threadIdx.x & 31) == 0 && len > 0) atomicMax(mx, len);
+}
+
+// ------------------------------------------------------------------------------------------------
+// esuel: one thread per (element, local face).  Candidates are the elements around the face's
+// lowest-degree node (first minimum in local order, grid.pyx:479-488); a candidate matches when one of
+// its faces contains every node of this face (grid.pyx:502-512); first match in (esup order, local
+// face order) wins.  On conforming meshes the match is unique, so the reference's reverse write
+// esuel[jelem,l] = ielem (:517) is what the thread of (jelem,l) finds by itself.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_esuel(ElemTables tab, const int32_t *__restrict__ inpoel, const uint8_t *__restrict__ etype,
+                        const int32_t *__restrict__ esup_ptr, const int32_t *__restrict__ esup, i64 n_elems, int spe,
+                        int sfe, int32_t *__restrict__ esuel)
+{
+    i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_elems * sfe) return;
+    i64 e = idx / sfe;
+    int j = (int)(idx - e * sfe);
+    int t = etype[e];
+    if (j >= tab.nfael[t]) {
+        esuel[idx] = -1;
+        return;
+    }
+    int nj = tab.lnofa[t][j];
+    int mine[NPB_MX_PF];
+#pragma unroll
+    for (int o = 0; o < NPB_MX_PF; o++) mine[o] = (o < nj) ? inpoel[e * spe + tab.lpofa[t][j][o]] : -2;
+    int point = mine[0];
+    int nmin = esup_ptr[point + 1] - esup_ptr[point];
+#pragma unroll
+    for (int k = 1; k < NPB_MX_PF; k++) {
+        if (k < nj) {
+            int ne = esup_ptr[mine[k] + 1] - esup_ptr[mine[k]];
+            if (ne < nmin) {
+                point = mine[k];
+                nmin = ne;
+            }
+        }
+    }
+    int res = -1;
+    int qb = esup_ptr[point], qe = esup_ptr[point + 1];
+    for (int q = qb; q < qe && res < 0; q++) {
+        int je = esup[q];
+        if (je == (int)e) continue;
+        int jt = etype[je];
+        const int32_t *rowj = inpoel + (i64)je * spe;
+        int nf = tab.nfael[jt];
+        for (int l = 0; l < nf; l++) {
+            int eq = 0;
+            int nl = tab.lnofa[jt][l];
+            for (int m = 0; m < nl; m++) {
+                int qn = rowj[tab.lpofa[jt][l][m]];
+                bool hit = false;
+#pragma unroll
+                for (int o = 0; o < NPB_MX_PF; o++) hit = hit || (qn == mine[o]);
+                eq += hit ? 1 : 0;
+            }
+            if (eq == nj) {
+                res = je;
+                break;
+            }
+        }
+    }
+    esuel[idx] = res;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Face numbering.  (e, j) owns its face iff it has no neighbour or e < neighbour: that is exactly the
+// face the reference's serial loop numbers when it first meets it (grid.pyx:315-334).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_owner_count(ElemTables tab, const uint8_t *__restrict__ etype, const int32_t *__restrict__ esuel,
+                              i64 n_elems, int sfe, int32_t *__restrict__ ownc)
+{
+    i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e > n_elems) return;
+    if (e == n_elems) {
+        ownc[e] = 0;
+        return;
+    }
+    int nf = tab.nfael[etype[e]];
+    int c = 0;
+    for (int j = 0; j < nf; j++) {
+        int nb = esuel[e * sfe + j];
+        c += (nb < 0 || (int)e < nb) ? 1 : 0;
+    }
+    ownc[e] = c;
+}
+
+// infael for every (e, j); owners also emit inpofa (owner's local ordering, grid.pyx:340-345),
+// esuf as the pair (owner, other), boundary tags (grid.pyx:434-444) and the node->face histogram.
+__global__ void k_faces(ElemTables tab, const int32_t *__restrict__ inpoel, const uint8_t *__restrict__ etype,
+                        const int32_t *__restrict__ esuel, const int32_t *__restrict__ fbase, i64 n_elems, int spe,
+                        int sfe, int32_t *__restrict__ infael, int32_t *__restrict__ inpofa, int2 *__restrict__ esuf2,
+                        uint8_t *__restrict__ bface, uint8_t *__restrict__ bpoint, int32_t *__restrict__ fcnt,
+                        int *__restrict__ n_bfaces)
+{
+    i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_elems) return;
+    int t = etype[e];
+    int nf = tab.nfael[t];
+    int rank = 0;
+    int base = fbase[e];
+    for (int j = 0; j < sfe; j++) {
+        if (j >= nf) {
+            infael[e * sfe + j] = -1;
+            continue;
+        }
+        int nb = esuel[e * sfe + j];
+        if (nb < 0 || (int)e < nb) {
+            int f = base + rank;
+            rank++;
+            infael[e * sfe + j] = f;
+            int nj = tab.lnofa[t][j];
+            int4 fn = make_int4(-1, -1, -1, -1);
+            int *fp = &fn.x;
+#pragma unroll
+            for (int k = 0; k < NPB_MX_PF; k++)
+                if (k < nj) {
+                    int p = inpoel[e * spe + tab.lpofa[t][j][k]];
+                    fp[k] = p;
+                    atomicAdd(&fcnt[p], 1);
+                    if (nb < 0) bpoint[p] = 1;
+                }
+            reinterpret_cast<int4 *>(inpofa)[f] = fn;
+            esuf2[f] = make_int2((int)e, nb);
+            bface[f] = nb < 0 ? 1 : 0;
+            if (nb < 0) atomicAdd(n_bfaces, 1);
+        } else {
+            // the owner is nb (< e): its id for this face = its base + number of owned faces before the
+            // first local face l with esuel[nb, l] == e (grid.pyx:331-334)
+            int kt = etype[nb];
+            int nfk = tab.nfael[kt];
+            int r = 0;
+            for (int l = 0; l < nfk; l++) {
+                int nbl = esuel[(i64)nb * sfe + l];
+                if (nbl == (int)e) break;
+                r += (nbl < 0 || nb < nbl) ? 1 : 0;
+            }
+            infael[e * sfe + j] = fbase[nb] + r;
+        }
+    }
+}
+
+// node -> face fill (rows sorted afterwards by k_sort_rows)
+__global__ void k_fill_fsup(const int32_t *__restrict__ inpofa, i64 n_faces, const int32_t *__restrict__ ptr,
+                            int32_t *__restrict__ cursor, int32_t *__restrict__ fsup)
+{
+    i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_faces * NPB_MX_PF) return;
+    int p = inpofa[idx];
+    if (p < 0) return;
+    int pos = atomicAdd(&cursor[p], 1);
+    fsup[(i64)ptr[p] + pos] = (int32_t)(idx / NPB_MX_PF);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host driver
+// ------------------------------------------------------------------------------------------------
+int npb_k1_build(npb_ctx *c, const i64 *h_conn, const i64 *h_types, const double *h_coords)
+{
+    const int T = 256;
+    cudaStream_t s = c->stream;
+    i64 ne = c->n_elems, np = c->n_points;
+    int spe = c->spe, sfe = c->sfe;
+
+    // ---- H2D of the reference-layout inputs, then compaction to int32 on the device ----
+    {
+        NpbTimer tm(c, "h2d_mesh");
+        i64 *d_conn = nullptr, *d_types = nullptr;
+        NPB_CUDA(cudaMalloc(&d_conn, sizeof(i64) * ne * NPB_MX_PE));
+        NPB_CUDA(cudaMalloc(&d_types, sizeof(i64) * ne));
+        NPB_CUDA(cudaMemcpyAsync(d_conn, h_conn, sizeof(i64) * ne * NPB_MX_PE, cudaMemcpyHostToDevice, s));
+        NPB_CUDA(cudaMemcpyAsync(d_types, h_types, sizeof(i64) * ne, cudaMemcpyHostToDevice, s));
+        NPB_TRY(npb_alloc(c, (void **)&c->inpoel, sizeof(int32_t) * ne * spe));
+        NPB_TRY(npb_alloc(c, (void **)&c->etype, ne));
+        NPB_TRY(npb_alloc(c, (void **)&c->coords, sizeof(double) * np * 3));
+        NPB_CUDA(cudaMemcpyAsync(c->coords, h_coords, sizeof(double) * np * 3, cudaMemcpyHostToDevice, s));
+        k_convert_conn<<<npb_blocks(ne * spe, T), T, 0, s>>>(d_conn, d_types, ne, spe, c->inpoel, c->etype);
+        NPB_LAUNCH(c);
+        tm.stop();
+        NPB_CUDA(cudaStreamSynchronize(s));
+        NPB_CUDA(cudaFree(d_conn));
+        NPB_CUDA(cudaFree(d_types));
+    }
+    NpbTimer tk1(c, "k1");
+    int *d_mx = c->counters;  // [0] = mx_epp, [1] = mx_fpp
+    NPB_CUDA(cudaMemsetAsync(d_mx, 0, sizeof(int) * 8, s));
+
+    // ---- esup ----
+    int32_t *cursor = nullptr;
+    {
+        NpbTimer tm(c, "k1_esup");
+        NPB_TRY(npb_alloc(c, (void **)&c->esup_ptr, sizeof(int32_t) * (np + 1)));
+        NPB_CUDA(cudaMalloc(&cursor, sizeof(int32_t) * (np + 1)));
+        NPB_CUDA(cudaMemsetAsync(c->esup_ptr, 0, sizeof(int32_t) * (np + 1), s));
+        k_count_nodes<<<npb_blocks(ne * spe, T), T, 0, s>>>(c->inpoel, ne * spe, c->esup_ptr);
+        NPB_LAUNCH(c);
+        NPB_TRY(npb_exclusive_scan_i32(c, c->esup_ptr, c->esup_ptr, np + 1));
+        int32_t total = 0;
+        NPB_CUDA(cudaMemcpyAsync(&total, c->esup_ptr + np, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        NPB_CUDA(cudaStreamSynchronize(s));
+        c->len_esup = total;
+        NPB_TRY(npb_alloc(c, (void **)&c->esup, sizeof(int32_t) * (size_t)(total > 0 ? total : 1)));
+        NPB_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (np + 1), s));
+        k_fill_rows<<<npb_blocks(ne * spe, T), T, 0, s>>>(c->inpoel, ne * spe, spe, c->esup_ptr, cursor, c->esup);
+        NPB_LAUNCH(c);
+        k_sort_rows<<<npb_blocks(np, T), T, 0, s>>>(c->esup_ptr, np, c->esup, d_mx + 0);
+        NPB_LAUNCH(c);
+        tm.stop();
+    }
+    // ---- esuel ----
+    {
+        NpbTimer tm(c, "k1_esuel");
+        NPB_TRY(npb_alloc(c, (void **)&c->esuel, sizeof(int32_t) * ne * sfe));
+        k_esuel<<<npb_blocks(ne * sfe, 128), 128, 0, s>>>(c->tab, c->inpoel, c->etype, c->esup_ptr, c->esup, ne, spe, sfe,
+                                                         c->esuel);
+        NPB_LAUNCH(c);
+        tm.stop();
+    }
+    // ---- faces: numbering, inpofa, esuf, tags, fsup histogram ----
+    int32_t *fbase = nullptr;
+    {
+        NpbTimer tm(c, "k1_faces");
+        NPB_CUDA(cudaMalloc(&fbase, sizeof(int32_t) * (ne + 1)));
+        k_owner_count<<<npb_blocks(ne + 1, T), T, 0, s>>>(c->tab, c->etype, c->esuel, ne, sfe, fbase);
+        NPB_LAUNCH(c);
+        NPB_TRY(npb_exclusive_scan_i32(c, fbase, fbase, ne + 1));
+        int32_t nfaces = 0;
+        NPB_CUDA(cudaMemcpyAsync(&nfaces, fbase + ne, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        NPB_CUDA(cudaStreamSynchronize(s));
+        c->n_faces = nfaces;
+        size_t nf1 = (size_t)(nfaces > 0 ? nfaces : 1);
+        NPB_TRY(npb_alloc(c, (void **)&c->infael, sizeof(int32_t) * ne * sfe));
+        NPB_TRY(npb_alloc(c, (void **)&c->inpofa, sizeof(int32_t) * nf1 * NPB_MX_PF));
+        NPB_TRY(npb_alloc(c, (void **)&c->esuf2, sizeof(int2) * nf1));
+        NPB_TRY(npb_alloc(c, (void **)&c->bface, nf1));
+        NPB_TRY(npb_alloc(c, (void **)&c->bpoint, (size_t)np));
+        NPB_TRY(npb_alloc(c, (void **)&c->fsup_ptr, sizeof(int32_t) * (np + 1)));
+        NPB_CUDA(cudaMemsetAsync(c->bpoint, 0, (size_t)np, s));
+        NPB_CUDA(cudaMemsetAsync(c->fsup_ptr, 0, sizeof(int32_t) * (np + 1), s));
+        k_faces<<<npb_blocks(ne, 128), 128, 0, s>>>(c->tab, c->inpoel, c->etype, c->esuel, fbase, ne, spe, sfe, c->infael,
+                                                   c->inpofa, c->esuf2, c->bface, c->bpoint, c->fsup_ptr, d_mx + 2);
+        NPB_LAUNCH(c);
+        tm.stop();
+    }
+    // ---- fsup ----
+    {
+        NpbTimer tm(c, "k1_fsup");
+        NPB_TRY(npb_exclusive_scan_i32(c, c->fsup_ptr, c->fsup_ptr, np + 1));
+        int32_t total = 0;
+        NPB_CUDA(cudaMemcpyAsync(&total, c->fsup_ptr + np, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        NPB_CUDA(cudaStreamSynchronize(s));
+        c->len_fsup = total;
+        NPB_TRY(npb_alloc(c, (void **)&c->fsup, sizeof(int32_t) * (size_t)(total > 0 ? total : 1)));
+        NPB_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (np + 1), s));
+        k_fill_fsup<<<npb_blocks(c->n_faces * NPB_MX_PF, T), T, 0, s>>>(c->inpofa, c->n_faces, c->fsup_ptr, cursor, c->fsup);
+        NPB_LAUNCH(c);
+        k_sort_rows<<<npb_blocks(np, T), T, 0, s>>>(c->fsup_ptr, np, c->fsup, d_mx + 1);
+        NPB_LAUNCH(c);
+        tm.stop();
+    }
+    int h_mx[3] = {0, 0, 0};
+    NPB_CUDA(cudaMemcpyAsync(h_mx, d_mx, sizeof(int) * 3, cudaMemcpyDeviceToHost, s));
+    NPB_CUDA(cudaStreamSynchronize(s));
+    c->mx_epp = h_mx[0];
+    c->mx_fpp = h_mx[1];
+    // esuf rows are [owner] or [owner, other] (grid.pyx:390-416)
+    c->len_esuf = 2 * c->n_faces - h_mx[2];
+    c->mx_epf = c->n_faces == 0 ? 0 : (h_mx[2] < c->n_faces ? 2 : 1);
+    NPB_CUDA(cudaFree(cursor));
+    NPB_CUDA(cudaFree(fbase));
+    // ---- geometry (k1_geometry.cu, compiled without FMA contraction) ----
+    NPB_TRY(npb_k1_geometry(c));
+    tk1.stop();
+    return NPB_OK;
+}

@@ -1,0 +1,149 @@
+// k4_shard.cu — node-partitioned sharding across the GPUs of one box (kernel group K4).
+//
+// No reference counterpart (the reference is one process).  Every rank holds the whole
+// mesh (K1 runs redundantly, cheaper than broadcasting it) and computes the CSR rows of one contiguous
+// node range; the row blocks are then all-gathered over NCCL (NVLink 5 / NVSwitch) straight into their
+// final positions: first the per-row counts and the neumann entries, then — once the scanned indptr
+// gives every block its global offset — the indices and data blocks.  Variable-size all-gather is
+// expressed as one grouped set of in-place ncclBroadcast calls, one per owner rank.
+// NCCL is dlopen'ed so that single-GPU use does not need it.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <string.h>
+#include "common.cuh"
+
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi g_nccl;
+
+static int load_nccl()
+{
+    if (g_nccl.handle) return NPB_OK;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *n : names) {
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) {
+        npb_set_error("cannot dlopen libnccl.so.2: %s", dlerror());
+        return NPB_ERR_NCCL;
+    }
+#define SYM(field, name)                                                     \
+    *(void **)(&g_nccl.field) = dlsym(h, name);                              \
+    if (!g_nccl.field) {                                                     \
+        npb_set_error("libnccl lacks symbol %s", name);                      \
+        return NPB_ERR_NCCL;                                                 \
+    }
+    SYM(GetUniqueId, "ncclGetUniqueId")
+    SYM(CommInitRank, "ncclCommInitRank")
+    SYM(CommDestroy, "ncclCommDestroy")
+    SYM(Broadcast, "ncclBroadcast")
+    SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    g_nccl.handle = h;
+    return NPB_OK;
+}
+
+#define NPB_NCCL(call)                                                                         \
+    do {                                                                                       \
+        ncclResult_t r__ = (call);                                                             \
+        if (r__ != ncclSuccess) {                                                              \
+            npb_set_error("NCCL error %s at %s:%d", g_nccl.GetErrorString(r__), __FILE__, __LINE__); \
+            return NPB_ERR_NCCL;                                                               \
+        }                                                                                      \
+    } while (0)
+
+extern "C" int npb_comm_unique_id(void *id_out)
+{
+    static_assert(sizeof(ncclUniqueId) == NPB_UNIQUE_ID_BYTES, "ncclUniqueId size");
+    if (!id_out) {
+        npb_set_error("npb_comm_unique_id: null output");
+        return NPB_ERR_ARG;
+    }
+    NPB_TRY(load_nccl());
+    ncclUniqueId id;
+    NPB_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(id_out, &id, sizeof(id));
+    return NPB_OK;
+}
+
+extern "C" int npb_comm_init(npb_ctx *c, const void *id, int rank, int world)
+{
+    if (!c || !id || world < 1 || rank < 0 || rank >= world) {
+        npb_set_error("npb_comm_init: bad arguments");
+        return NPB_ERR_ARG;
+    }
+    NPB_CUDA(cudaSetDevice(c->device));
+    if (world == 1) {
+        c->rank = 0;
+        c->world = 1;
+        return NPB_OK;
+    }
+    NPB_TRY(load_nccl());
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    ncclComm_t comm;
+    NPB_NCCL(g_nccl.CommInitRank(&comm, world, uid, rank));
+    c->comm = comm;
+    c->nccl = &g_nccl;
+    c->rank = rank;
+    c->world = world;
+    return NPB_OK;
+}
+
+int npb_comm_destroy(npb_ctx *c)
+{
+    if (c->comm && c->nccl) c->nccl->CommDestroy((ncclComm_t)c->comm);
+    c->comm = nullptr;
+    return NPB_OK;
+}
+
+// all-gather of rowcnt[lo_r:hi_r] and neumann[lo_r:hi_r] from their owners
+int npb_k4_gather_counts(npb_ctx *c)
+{
+    if (c->world == 1) return NPB_OK;
+    NcclApi *api = c->nccl;
+    ncclComm_t comm = (ncclComm_t)c->comm;
+    NPB_NCCL(api->GroupStart());
+    for (int r = 0; r < c->world; r++) {
+        i64 b = c->bounds[r], n = c->bounds[r + 1] - b;
+        if (n <= 0) continue;
+        NPB_NCCL(api->Broadcast(c->rowcnt + b, c->rowcnt + b, (size_t)n, ncclInt32, r, comm, c->stream));
+        NPB_NCCL(api->Broadcast(c->neumann + b, c->neumann + b, (size_t)n, ncclFloat64, r, comm, c->stream));
+    }
+    NPB_NCCL(api->GroupEnd());
+    return NPB_OK;
+}
+
+// all-gather of the indices / data row blocks; nnz offsets of the blocks come from the scanned indptr
+int npb_k4_gather_blocks(npb_ctx *c)
+{
+    if (c->world == 1) return NPB_OK;
+    NcclApi *api = c->nccl;
+    ncclComm_t comm = (ncclComm_t)c->comm;
+    std::vector<int32_t> off(c->world + 1);
+    for (int r = 0; r <= c->world; r++)
+        NPB_CUDA(cudaMemcpyAsync(&off[r], c->indptr + c->bounds[r], sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    NPB_CUDA(cudaStreamSynchronize(c->stream));
+    NPB_NCCL(api->GroupStart());
+    for (int r = 0; r < c->world; r++) {
+        i64 b = off[r], n = (i64)off[r + 1] - off[r];
+        if (n <= 0) continue;
+        NPB_NCCL(api->Broadcast(c->indices + b, c->indices + b, (size_t)n, ncclInt32, r, comm, c->stream));
+        NPB_NCCL(api->Broadcast(c->data + b, c->data + b, (size_t)n, ncclFloat64, r, comm, c->stream));
+    }
+    NPB_NCCL(api->GroupEnd());
+    return NPB_OK;
+}

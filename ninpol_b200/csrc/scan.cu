@@ -1,0 +1,62 @@
+// scan.cu — prefix sums, maxima and stream compaction (CUB device primitives compiled into this
+// library; the only translation unit that instantiates CUB, to keep build times down).
+// These are the "scan" steps of the counting-sort / two-pass-emit formulations of K1 and K3.
+#include <cub/device/device_reduce.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include "common.cuh"
+
+int npb_exclusive_scan_i32(npb_ctx *c, const int32_t *in, int32_t *out, i64 n)
+{
+    if (n <= 0) return NPB_OK;
+    if (n >= (1ll << 31)) {
+        npb_set_error("scan length %lld exceeds the 32-bit range", n);
+        return NPB_ERR_RANGE;
+    }
+    size_t need = 0;
+    NPB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, in, out, (int)n, c->stream));
+    NPB_TRY(npb_ensure(&c->scratch, &c->scratch_cap, need));
+    NPB_CUDA(cub::DeviceScan::ExclusiveSum(c->scratch, need, in, out, (int)n, c->stream));
+    c->launches += 2;  // CUB's decoupled look-back scan: init + scan kernels
+    return NPB_OK;
+}
+
+int npb_max_i32(npb_ctx *c, const int32_t *in, i64 n, int32_t *host_out)
+{
+    *host_out = 0;
+    if (n <= 0) return NPB_OK;
+    size_t need = 0;
+    int32_t *d_out = (int32_t *)(c->counters + 16);
+    NPB_CUDA(cub::DeviceReduce::Max(nullptr, need, in, d_out, (int)n, c->stream));
+    NPB_TRY(npb_ensure(&c->scratch, &c->scratch_cap, need));
+    NPB_CUDA(cub::DeviceReduce::Max(c->scratch, need, in, d_out, (int)n, c->stream));
+    c->launches += 2;
+    NPB_CUDA(cudaMemcpyAsync(host_out, d_out, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    NPB_CUDA(cudaStreamSynchronize(c->stream));
+    return NPB_OK;
+}
+
+struct ClassIs {
+    const uint8_t *cls;
+    int which;
+    __host__ __device__ bool operator()(const int &i) const { return cls[i] == which; }
+};
+
+// out <- ascending node ids p in [lo, hi) with cls[p] == which
+int npb_select_class(npb_ctx *c, const uint8_t *cls, i64 lo, i64 hi, int which, int32_t *out, int *host_count)
+{
+    *host_count = 0;
+    if (hi <= lo) return NPB_OK;
+    thrust::counting_iterator<int> it((int)lo);
+    ClassIs pred{cls, which};
+    int *d_num = c->counters + 17;
+    size_t need = 0;
+    NPB_CUDA(cub::DeviceSelect::If(nullptr, need, it, out, d_num, (int)(hi - lo), pred, c->stream));
+    NPB_TRY(npb_ensure(&c->scratch, &c->scratch_cap, need));
+    NPB_CUDA(cub::DeviceSelect::If(c->scratch, need, it, out, d_num, (int)(hi - lo), pred, c->stream));
+    c->launches += 2;
+    NPB_CUDA(cudaMemcpyAsync(host_count, d_num, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    NPB_CUDA(cudaStreamSynchronize(c->stream));
+    return NPB_OK;
+}

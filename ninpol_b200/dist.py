@@ -1,0 +1,127 @@
+"""Multi-GPU wiring: one process per GPU, node-partitioned rows (kernel group K4, host side).
+
+The device side (NCCL all-gather of the CSR row blocks) lives in csrc/k4_shard.cu; this module holds
+the host logic that is independent of CUDA and therefore testable on CPU: reading the launcher's
+environment, shipping the 128-byte NCCL unique id from rank 0 to the other ranks over a plain TCP
+socket, and cutting the node range into contiguous per-rank blocks balanced on a cost prefix sum.
+"""
+import os
+import socket
+import struct
+import time
+
+import numpy as np
+
+
+class Comm:
+    """Rank / world size / NCCL unique id of this process."""
+
+    def __init__(self, rank=0, world=1, local_rank=None, unique_id=None):
+        self.rank, self.world = int(rank), int(world)
+        self.local_rank = self.rank if local_rank is None else int(local_rank)
+        self.unique_id = unique_id
+
+
+def exchange_bytes(payload, rank, world, addr="127.0.0.1", port=29517, timeout=300.0):
+    """Rank 0 serves `payload` to the world-1 other ranks; they return what they received."""
+    if world == 1:
+        return payload
+    if rank == 0:
+        srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+        srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+        srv.bind((addr, port))
+        srv.listen(world)
+        srv.settimeout(timeout)
+        for _ in range(world - 1):
+            conn, _a = srv.accept()
+            conn.sendall(struct.pack("<I", len(payload)) + payload)
+            conn.close()
+        srv.close()
+        return payload
+    deadline = time.time() + timeout
+    while True:
+        try:
+            s = socket.create_connection((addr, port), timeout=5.0)
+            break
+        except OSError:
+            if time.time() > deadline:
+                raise
+            time.sleep(0.05)
+    buf = b""
+    while len(buf) < 4:
+        buf += s.recv(4 - len(buf))
+    n = struct.unpack("<I", buf)[0]
+    out = b""
+    while len(out) < n:
+        chunk = s.recv(n - len(out))
+        if not chunk:
+            raise ConnectionError("unique-id exchange: peer closed")
+        out += chunk
+    s.close()
+    return out
+
+
+def init_from_env(get_unique_id=None, port_offset=17):
+    """Build a Comm from torchrun-style variables (RANK, WORLD_SIZE, LOCAL_RANK, MASTER_ADDR,
+    MASTER_PORT).  `get_unique_id` is called on rank 0 only (defaults to the library's NCCL id)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    if world == 1:
+        return Comm(0, 1, local, None)
+    addr = os.environ.get("MASTER_ADDR", "127.0.0.1")
+    port = int(os.environ.get("MASTER_PORT", "29500")) + port_offset
+    payload = b""
+    if rank == 0:
+        if get_unique_id is None:
+            from . import _capi
+            get_unique_id = _capi.comm_unique_id
+        payload = get_unique_id()
+    uid = exchange_bytes(payload, rank, world, addr, port)
+    return Comm(rank, world, local, uid)
+
+
+def node_cost(method, n_elem_per_node, processed):
+    """Relative cost of one node: IDW/LS stream ~40 E + 42 bytes; GLS factors a
+    ~5.5E x 3E system, ~E^3 flops.  Skipped (Dirichlet) nodes cost a constant."""
+    E = np.asarray(n_elem_per_node, dtype=np.float64)
+    if method == "gls":
+        c = E ** 3 + 50.0 * E + 20.0
+    else:
+        c = 40.0 * E + 42.0
+    return np.where(processed, c, 18.0)
+
+
+def partition_nodes(cost, world):
+    """bounds[world+1]: contiguous node ranges with (nearly) equal summed cost."""
+    cost = np.asarray(cost, dtype=np.float64)
+    n = len(cost)
+    if world == 1:
+        return np.array([0, n], dtype=np.int64)
+    cum = np.cumsum(cost)
+    total = cum[-1] if n else 0.0
+    targets = total * np.arange(1, world) / world
+    cuts = np.searchsorted(cum, targets, side="left") + 1
+    bounds = np.concatenate([[0], np.minimum(cuts, n), [n]]).astype(np.int64)
+    return np.maximum.accumulate(bounds)
+
+
+def assemble_row_blocks(blocks, n_points):
+    """Host-side statement of what K4 does on the device: concatenate per-rank CSR row blocks
+    (row counts, indices, data, neumann) of contiguous node ranges into the global arrays.
+    `blocks` = list of dicts with keys lo, hi, counts, indices, data, neumann, ordered by rank."""
+    counts = np.zeros(n_points, dtype=np.int32)
+    neumann = np.zeros(n_points, dtype=np.float64)
+    for b in blocks:
+        counts[b["lo"]:b["hi"]] = b["counts"]
+        neumann[b["lo"]:b["hi"]] = b["neumann"]
+    indptr = np.zeros(n_points + 1, dtype=np.int64)
+    np.cumsum(counts, out=indptr[1:])
+    nnz = int(indptr[-1])
+    indices = np.empty(nnz, dtype=np.int32)
+    data = np.empty(nnz, dtype=np.float64)
+    for b in blocks:
+        s, e = int(indptr[b["lo"]]), int(indptr[b["hi"]])
+        indices[s:e] = b["indices"]
+        data[s:e] = b["data"]
+    return indptr.astype(np.int32), indices, data, neumann

@@ -1,0 +1,393 @@
+"""Interpolator — drop-in for `ninpol.Interpolator` on one B200 (or one per process for multi-GPU).
+
+Same constructor keywords, methods and attributes as the reference class
+(ninpol/_interpolator/interpolator.pyx:35-670, interpolator.pxd:27-58):
+
+    I = Interpolator(name="interpolator", logging=False, build_edges=False)
+    I.load_mesh(mesh_obj=mesh)                       # or filename=... when meshio is installed
+    W, neumann = I.interpolate("pressure", "gls")    # scipy CSR (n_nodes, n_elements), ndarray (n_nodes,)
+    I.supported_methods                              # {"gls": ..., "idw": ..., "ls": ...}
+
+The host side only ingests the mesh object (vectorised numpy instead of the reference's per-item Python
+loops, same outputs) and hands plain arrays to libninpol_b200.so through ctypes; connectivity,
+geometry, the per-node weights and the CSR emit all run on the GPU.  There is no CPU fallback.
+"""
+import os
+import pickle
+import tempfile
+import time
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _capi
+from . import dist as _dist
+from . import element_tables as et
+from .grid import Grid
+
+DTYPE_I = np.int64
+DTYPE_F = np.float64
+
+
+class _Logger:
+    """`[TYPE ] (HH:MM:SS) msg` lines like the reference Logger (logger.pyx:47-56); stdout only."""
+
+    def __init__(self, name, logging=False):
+        self.name, self.logging = name, logging
+
+    def log(self, msg, kind="INFO"):
+        if self.logging:
+            print(f"[{kind:<5}] ({time.strftime('%H:%M:%S')}) {self.name}: {msg}", flush=True)
+
+
+class _Method:
+    """Host mirror of one interpolation plug-in (IDWInterpolation / LSInterpolation /
+    GLSInterpolation).  `prepare` has the reference plug-in signature (idw.pxd:19-24, ls.pxd:20-25,
+    gls.pxd:22-27): it fills the caller's dense zero-initialised `weights[n_target, MX_ELEMENTS_PER_POINT]`
+    (column k of row p <-> esup[esup_ptr[p]+k]) and `neumann_ws[n_target]`."""
+
+    def __init__(self, owner, method, logging=False):
+        self._owner, self.method, self.logging = owner, method, logging
+        self.logger = _Logger(method.upper(), logging)
+
+    def prepare(self, grid, cells_data, points_data, faces_data, variable_to_index, variable, target_points,
+                weights, neumann_ws):
+        I = self._owner
+        if grid is not I.grid:
+            raise ValueError("this plug-in is bound to its Interpolator's grid")
+        I._check_targets(target_points)
+        I._stage_inputs(self.method, variable, variable_to_index, cells_data, points_data)
+        indptr, indices, data, neumann = I._run(self.method)
+        # CSR rows hold w + neumann_ws (interpolator.pyx:618); the plug-in contract is w itself
+        esup_ptr, esup = np.asarray(grid.esup_ptr), np.asarray(grid.esup)
+        rows = np.repeat(np.arange(grid.n_points, dtype=np.int64), np.diff(indptr))
+        # position of every kept entry inside its (ascending) esup row
+        stride = grid.n_elems + 1
+        allkey = np.repeat(np.arange(grid.n_points, dtype=np.int64), np.diff(esup_ptr)) * stride + esup
+        pos = np.searchsorted(allkey, rows * stride + indices) - esup_ptr[rows]
+        weights[rows, pos] = data - neumann[rows]
+        neumann_ws[:] = neumann
+
+    __call__ = prepare
+
+
+class Interpolator:
+    def __init__(self, name="interpolator", logging=False, build_edges=False, device=None, comm=None):
+        self.point_ordering = et.POINT_ORDERING
+        self.is_grid_initialized = False
+        self.build_edges = build_edges
+        self.gls = _Method(self, "gls", logging)
+        self.idw = _Method(self, "idw", logging)
+        self.ls = _Method(self, "ls", logging)
+        # same keys, same order as interpolator.pyx:60-64
+        self.supported_methods = {"gls": self.gls.prepare, "idw": self.idw.prepare, "ls": self.ls.prepare}
+        self.variable_to_index = {"points": {}, "cells": {}, "faces": {}}
+        self.types_per_dimension = {k: list(v) for k, v in et.TYPES_PER_DIMENSION.items()}
+        self.cells_data = np.zeros((1, 1), dtype=DTYPE_F)
+        self.cells_data_dimensions = np.zeros(1, dtype=DTYPE_I)
+        self.points_data = np.zeros((1, 1), dtype=DTYPE_F)
+        self.points_data_dimensions = np.zeros(1, dtype=DTYPE_I)
+        self.faces_data = np.zeros((1, 1), dtype=DTYPE_F)
+        self.faces_data_dimensions = np.zeros(1, dtype=DTYPE_I)
+        self.logging = logging
+        self.logger = _Logger(name, logging)
+        self.CACHE_PATH = tempfile.gettempdir()
+        self.mesh_obj = None
+        self.grid = None
+        self.points_coords = None
+        # device side
+        self.comm = comm if comm is not None else _dist.Comm(0, 1)
+        if device is None:
+            device = self.comm.local_rank if self.comm.world > 1 else 0
+        self._ctx = _capi.Context(device)      # raises when the library or the GPU is missing
+        if self.comm.world > 1:
+            self._ctx.comm_init(self.comm.unique_id, self.comm.rank, self.comm.world)
+        self._staged = None
+        self._partition_key = None
+        self.last_timings = {}
+
+    # ------------------------------------------------------------------------------------------
+    # cache helpers (interpolator.pyx:93-111) — inputs-only pickle cache, file meshes only
+    # ------------------------------------------------------------------------------------------
+    def is_cached(self, filename):
+        if filename == "":
+            return None
+        little_hash = hex(os.path.getsize(filename))
+        cache_name = filename.split(os.path.sep)[-1].split(".")[0] + little_hash + ".pkl"
+        final_path = os.path.join(self.CACHE_PATH, cache_name)
+        return final_path if os.path.exists(final_path) else None
+
+    # ------------------------------------------------------------------------------------------
+    # load_mesh (interpolator.pyx:168-252)
+    # ------------------------------------------------------------------------------------------
+    def load_mesh(self, filename="", mesh_obj=None):
+        if filename == "" and mesh_obj is None:
+            raise ValueError("Filename for the mesh or meshio.Mesh object must be provided.")
+        cached = self.is_cached(filename)
+        if cached:
+            self.logger.log("Loading mesh from cache")
+            with open(cached, "rb") as f:
+                cache = pickle.load(f)
+            args = cache["grid"]
+            ic = cache["interpolator"]
+            self.cells_data, self.cells_data_dimensions = ic["cells_data"], ic["cells_data_dimensions"]
+            self.points_data, self.points_data_dimensions = ic["points_data"], ic["points_data_dimensions"]
+            self.faces_data, self.faces_data_dimensions = ic["faces_data"], ic["faces_data_dimensions"]
+            self.variable_to_index, self.points_coords = ic["variable_to_index"], ic["points_coords"]
+        else:
+            if filename != "":
+                self.logger.log(f"Reading mesh from {filename}")
+                try:
+                    import meshio
+                except ImportError as e:
+                    raise ImportError("reading mesh files needs the `meshio` package; pass mesh_obj= instead") from e
+                self.mesh_obj = meshio.read(filename)
+            else:
+                self.logger.log("Using mesh object")
+                self.mesh_obj = mesh_obj
+            args = self.process_mesh(self.mesh_obj)
+            self.points_coords = np.asarray(self.mesh_obj.points).astype(DTYPE_F)
+        dim, n_elems, n_points, npoel, nfael, lnofa, lpofa, nedel, lpoed, connectivity, element_types = args[:11]
+        coords = np.asarray(self.points_coords, dtype=DTYPE_F)
+        if coords.shape[1] != 3:
+            # the reference keeps 2-column coordinates as they are (grid.pyx:661-667) and then reads a
+            # third column out of bounds in LS/GLS; the device layout is [n,3], zero padded
+            c3 = np.zeros((coords.shape[0], 3), dtype=DTYPE_F)
+            c3[:, :coords.shape[1]] = coords
+            coords = c3
+        t0 = time.time()
+        self._ctx.load_mesh(dim, n_elems, n_points, connectivity, element_types, npoel, nfael, lnofa, lpofa, nedel,
+                            lpoed, coords, self.build_edges)
+        self.grid = Grid(self._ctx, (npoel, nfael, lnofa, lpofa, nedel, lpoed), self.logging, self.build_edges)
+        self.logger.log(f"Grid built in {time.time() - t0:.2f} seconds")
+        self.last_timings["load_mesh_device_ms"] = self._ctx.timing_or("k1")
+        self.last_timings["load_mesh_h2d_ms"] = self._ctx.timing_or("h2d_mesh")
+        if not cached:
+            t0 = time.time()
+            self.variable_to_index = {"points": {}, "cells": {}, "faces": {}}
+            if self.mesh_obj.cell_data:
+                self.load_cell_data()
+            else:
+                self.cells_data = np.zeros((1, 1), dtype=DTYPE_F)
+                self.cells_data_dimensions = np.zeros(1, dtype=DTYPE_I)
+            if self.mesh_obj.point_data:
+                self.load_point_data()
+            else:
+                self.points_data = np.zeros((1, 1), dtype=DTYPE_F)
+                self.points_data_dimensions = np.zeros(1, dtype=DTYPE_I)
+            self.logger.log(f"Data loaded in {time.time() - t0:.2f} seconds")
+        self.is_grid_initialized = True
+        self._staged = None
+        self._partition_key = None
+        self.logger.log(f"Mesh loaded successfully: {n_points} points and {n_elems} elements.")
+        if not cached and filename != "":
+            little_hash = hex(os.path.getsize(filename))
+            pkl_name = filename.split(os.path.sep)[-1].split(".")[0] + little_hash + ".pkl"
+            final_path = os.path.join(self.CACHE_PATH, pkl_name)
+            with open(final_path, "wb") as f:
+                pickle.dump(self.make_cache(args), f)
+            self.logger.log(f"Caching grid to {final_path}")
+
+    def make_cache(self, args):
+        return {"grid": tuple(args),
+                "interpolator": {"cells_data": np.asarray(self.cells_data),
+                                 "cells_data_dimensions": np.asarray(self.cells_data_dimensions),
+                                 "points_data": np.asarray(self.points_data),
+                                 "points_data_dimensions": np.asarray(self.points_data_dimensions),
+                                 "faces_data": np.asarray(self.faces_data),
+                                 "faces_data_dimensions": np.asarray(self.faces_data_dimensions),
+                                 "variable_to_index": self.variable_to_index,
+                                 "points_coords": np.asarray(self.points_coords)}}
+
+    # ------------------------------------------------------------------------------------------
+    # process_mesh (interpolator.pyx:255-369), vectorised
+    # ------------------------------------------------------------------------------------------
+    def process_mesh(self, mesh):
+        dim = 1
+        for blk in mesh.cells:
+            for dimension, names in self.types_per_dimension.items():
+                if blk.type in names:
+                    dim = max(dim, dimension)
+        tables = et.tables_for_dim(dim, self.point_ordering)
+        blocks = [b for b in mesh.cells if b.type in self.types_per_dimension[dim]]
+        n_elems = int(sum(len(b.data) for b in blocks))
+        n_points = int(np.asarray(mesh.points).shape[0])
+        connectivity = -np.ones((n_elems, et.MAX_POINTS_PER_ELEMENT), dtype=DTYPE_I)
+        element_types = -np.ones(n_elems, dtype=DTYPE_I)
+        at = 0
+        for b in blocks:
+            d = np.asarray(b.data)
+            connectivity[at:at + len(d), :d.shape[1]] = d
+            element_types[at:at + len(d)] = self.point_ordering["elements"][b.type]["element_type"]
+            at += len(d)
+        return (dim, n_elems, n_points) + tuple(tables) + (connectivity, element_types, self.logging, self.build_edges)
+
+    # ------------------------------------------------------------------------------------------
+    # load_data / load_cell_data / load_point_data (interpolator.pyx:372-454), vectorised
+    # ------------------------------------------------------------------------------------------
+    def load_data(self, data_dict, data_type):
+        n_items = self.grid.n_elems if data_type == "cells" else self.grid.n_points
+        dims = np.zeros(len(data_dict), dtype=DTYPE_I)
+        max_shape = 1
+        for index, variable in enumerate(data_dict):
+            a = np.asarray(data_dict[variable])
+            cur = a.shape[1] if a.ndim > 1 else 1
+            max_shape = max(max_shape, cur)
+            self.variable_to_index[data_type][variable] = index
+            dims[index] = cur
+        out = np.zeros((len(data_dict), n_items * max_shape), dtype=DTYPE_F)
+        for variable in data_dict:
+            index = self.variable_to_index[data_type][variable]
+            a = np.asarray(data_dict[variable])
+            if dims[index] == 1:
+                out[index, :n_items] = a[:n_items] if a.ndim == 1 else a[:n_items, 0]
+            else:
+                out[index, :n_items * dims[index]] = a[:n_items].reshape(-1)
+        if data_type == "cells":
+            self.cells_data_dimensions, self.cells_data = dims, out
+        else:
+            self.points_data_dimensions, self.points_data = dims, out
+
+    def load_cell_data(self):
+        dim = self.grid.dim
+        cell_data_dict = self.mesh_obj.cell_data_dict
+        cell_data = {}
+        for variable in cell_data_dict:
+            parts = [np.asarray(v) for t, v in cell_data_dict[variable].items() if t in self.types_per_dimension[dim]]
+            cell_data[variable] = np.concatenate(parts) if parts else np.zeros(0)
+            if variable == "permeability":
+                cell_data["diff_mag"] = self.compute_diffusion_magnitude(cell_data["permeability"])
+        self.load_data(cell_data, "cells")
+
+    def load_point_data(self):
+        self.load_data(self.mesh_obj.point_data, "points")
+
+    def load_face_data(self, data_dict, face_connectivity=None):
+        """interpolator.pyx:456-499 (scalar face data; optional remap through a user inpofa)."""
+        n_faces = self.grid.n_faces
+        face_to_grid = np.arange(n_faces, dtype=DTYPE_I)
+        if face_connectivity is not None and len(face_connectivity) > 0 and np.asarray(face_connectivity).size > 0:
+            A = np.ascontiguousarray(face_connectivity, dtype=DTYPE_I)
+            B = np.ascontiguousarray(self.grid.inpofa, dtype=DTYPE_I)
+            Av = A.view([("", A.dtype)] * A.shape[1]).ravel()
+            Bv = B.view([("", B.dtype)] * B.shape[1]).ravel()
+            order = np.argsort(Bv)
+            face_to_grid = order[np.searchsorted(Bv[order], Av)]
+        self.faces_data = np.zeros((len(data_dict), n_faces), dtype=DTYPE_F)
+        self.faces_data_dimensions = np.zeros(len(data_dict), dtype=DTYPE_I)
+        for i, variable in enumerate(data_dict):
+            a = np.asarray(data_dict[variable])
+            self.variable_to_index["faces"][variable] = i
+            self.faces_data_dimensions[i] = a.shape[1] if a.ndim > 1 else 1
+            self.faces_data[i] = a[face_to_grid].astype(DTYPE_F).reshape(n_faces, -1)[:, 0]
+
+    @staticmethod
+    def compute_diffusion_magnitude(permeability):
+        """interpolator.pyx:501-509 as the RELEASE build evaluates it: `1 / 3` is C integer division
+        (cdivision=True, setup.py:100-108), so det**0 == 1 and diff_mag = (1 - 3/tr K)^2."""
+        Ks = np.reshape(np.asarray(permeability, dtype=DTYPE_F), (len(permeability), 3, 3))
+        detKs = np.linalg.det(Ks)
+        trKs = np.trace(Ks, axis1=1, axis2=2)
+        return (1 - (3 * (detKs ** 0) / trKs)) ** 2
+
+    def get_dict(self):
+        return {"point_ordering": self.point_ordering, "variable_to_index": self.variable_to_index,
+                "cells_data": np.asarray(self.cells_data),
+                "cells_data_dimensions": np.asarray(self.cells_data_dimensions),
+                "points_data": np.asarray(self.points_data),
+                "points_data_dimensions": np.asarray(self.points_data_dimensions)}
+
+    def get_data(self, data_type, index, variable):
+        kind = "cells" if data_type == "cells" else "points"
+        if variable not in self.variable_to_index[kind]:
+            raise ValueError(f"Variable '{variable}' not found in {kind} data.")
+        src = self.cells_data if kind == "cells" else self.points_data
+        return np.asarray(src[self.variable_to_index[kind][variable]])[index]
+
+    # ------------------------------------------------------------------------------------------
+    # interpolate (interpolator.pyx:549-629)
+    # ------------------------------------------------------------------------------------------
+    def _check_targets(self, target_points):
+        n = self.grid.n_points
+        tp = np.asarray(target_points)
+        if len(tp) == 0:
+            return
+        if len(tp) != n or not np.array_equal(tp, np.arange(n)):
+            # the reference indexes a (n_target, n_elems) matrix with global point ids and raises
+            # ValueError from scipy for every strict subset
+            raise ValueError("target_points subsets are not supported: the reference builds an inconsistent "
+                             "(n_target, n_elems) matrix for them and fails in scipy; pass all nodes or nothing")
+
+    def _stage_inputs(self, method, variable, variable_to_index, cells_data, points_data):
+        """Uploads what the plug-in of `method` reads for `variable` (idw.pyx:27-28, ls.pyx:28-29,
+        gls.pyx:47-59).  Missing names raise KeyError like the reference's dict lookups."""
+        g = self.grid
+        key = (method == "gls", variable, id(cells_data), id(points_data))
+        flag_index = None
+        if method == "gls":
+            permeability_index = variable_to_index["cells"]["permeability"]
+            diff_mag_index = variable_to_index["cells"]["diff_mag"]
+            flag_index = variable_to_index["points"]["neumann_flag_" + variable]
+            variable_to_index["points"]["neumann_" + variable]   # looked up (KeyError) but dead
+        else:
+            flag_index = variable_to_index["points"]["neumann_flag_" + variable]
+        if self._staged == key:
+            return
+        flags = np.asarray(points_data[flag_index])[:g.n_points].astype(DTYPE_I)
+        self._ctx.set_point_flags(flags)
+        if method == "gls":
+            self._ctx.set_cell_field("permeability", np.asarray(cells_data[permeability_index])[:g.n_elems * 9])
+            self._ctx.set_cell_field("diff_mag", np.asarray(cells_data[diff_mag_index])[:g.n_elems])
+        self._flags_host = flags
+        self._staged = key
+
+    def _set_partition(self, method):
+        if self.comm.world == 1:
+            return
+        key = (method == "gls", self._staged)
+        if self._partition_key == key:
+            return
+        g = self.grid
+        E = np.diff(np.asarray(g.esup_ptr))
+        processed = ~((np.asarray(g.boundary_points) != 0) & (self._flags_host == 0))
+        bounds = _dist.partition_nodes(_dist.node_cost(method, E, processed), self.comm.world)
+        self._ctx.set_partition(bounds)
+        self._partition_key = key
+        self.partition_bounds = bounds
+
+    def _run(self, method):
+        g = self.grid
+        self._set_partition(method)
+        nnz = self._ctx.interpolate_count(method)
+        n_points = g.n_points
+        indptr = np.empty(n_points + 1, dtype=np.int32)
+        indices = np.empty(nnz, dtype=np.int32)
+        data = np.empty(nnz, dtype=np.float64)
+        neumann = np.empty(n_points, dtype=np.float64)
+        self._ctx.interpolate_fetch(indptr, indices, data, neumann)
+        t = self._ctx.timing_or
+        self.last_timings.update({"k2_ms": t("k2"), "k3_count_ms": t("k3_count"), "k3_fill_ms": t("k3_fill"),
+                                  "k4_gather_ms": t("k4_gather") if self.comm.world > 1 else 0.0,
+                                  "d2h_csr_ms": t("d2h_csr"), "nnz": nnz})
+        return indptr, indices, data, neumann
+
+    def interpolate(self, variable, method, target_points=np.array([], dtype=DTYPE_I)):
+        if not self.is_grid_initialized:
+            raise ValueError("Grid not initialized. Please load a mesh first.")
+        if method not in self.supported_methods:
+            raise ValueError(f"Method '{method}' not supported. Supported methods are: {list(self.supported_methods.keys())}")
+        if variable not in self.variable_to_index["cells"]:
+            raise ValueError(f"Variable '{variable}' not found in cells data. Point -> Cell interpolation not supported yet.")
+        data_index = self.variable_to_index["cells"][variable]
+        if self.cells_data_dimensions[data_index] > 1:
+            raise ValueError(f"Variable '{variable}' has more than one dimension. Vector data not supported yet.")
+        self._check_targets(target_points)
+        self.logger.log(f"Interpolating variable '{variable}' using method '{method}'")
+        self._stage_inputs(method, variable, self.variable_to_index, self.cells_data, self.points_data)
+        indptr, indices, data, neumann = self._run(method)
+        g = self.grid
+        # the device emitted canonical CSR (sorted, zero-free, int32 index arrays): no conversion, no copy
+        W = sp.csr_matrix((data, indices, indptr), shape=(g.n_points, g.n_elems), copy=False)
+        W.has_sorted_indices = True
+        W.has_canonical_format = True
+        return W, neumann

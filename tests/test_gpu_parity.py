@@ -1,0 +1,141 @@
+"""Parity of the CUDA path (through the C ABI, via ninpol_b200.Interpolator) against the oracle.
+
+Bar (BASELINE.json north_star): bit-exact for every connectivity / geometry array, the
+CSR structure of all three methods and the IDW / LS values (NaN positions included); GLS weights and
+neumann within 1e-12, measured row-normwise (|w - w_ref| / max_row |w_ref|).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GRID_ARRAYS = ("inpoel", "element_types", "esup", "esup_ptr", "psup", "psup_ptr", "esuel", "infael", "inpofa", "fsup",
+               "fsup_ptr", "esuf", "esuf_ptr", "boundary_faces", "boundary_points", "point_coords", "centroids",
+               "faces_centers", "normal_faces", "faces_areas")
+GRID_SCALARS = ("n_elems", "n_points", "n_faces", "MX_ELEMENTS_PER_POINT", "MX_POINTS_PER_POINT",
+                "MX_ELEMENTS_PER_FACE", "MX_FACES_PER_POINT")
+GLS_TOL = 1e-12
+
+CASES = [("tet", 7, {}), ("hex", 8, {}), ("mixed", 8, {"a": 2, "b": 4}), ("tet", 14, {}), ("hex", 20, {}),
+         ("hex", 6, {"perturb": 0.2}), ("mixed", 12, {"a": 3, "b": 6}), ("tet", 3, {}), ("hex", 1, {}), ("tet", 1, {})]
+
+
+def _pair(kind, n, kw):
+    import ninpol_b200
+    import oracle
+    from ninpol_b200 import meshgen
+    mesh = meshgen.make_case(kind, n, **kw)
+    I = ninpol_b200.Interpolator()
+    I.load_mesh(mesh_obj=mesh)
+    O = oracle.OracleInterpolator().load_mesh(mesh)
+    return I, O
+
+
+def gls_errors(W, Wo):
+    rows = np.repeat(np.arange(W.shape[0]), np.diff(W.indptr))
+    scale = np.zeros(W.shape[0])
+    np.maximum.at(scale, rows, np.abs(Wo.data))
+    scale[scale == 0] = 1.0
+    return float(np.max(np.abs(W.data - Wo.data) / scale[rows])) if W.nnz else 0.0
+
+
+@pytest.mark.parametrize("kind,n,kw", CASES)
+def test_connectivity_and_geometry_bit_exact(kind, n, kw):
+    I, O = _pair(kind, n, kw)
+    for s in GRID_SCALARS:
+        assert getattr(I.grid, s) == getattr(O.grid, s), s
+    for name in GRID_ARRAYS:
+        a, b = np.asarray(getattr(I.grid, name)), np.asarray(getattr(O.grid, name))
+        assert a.dtype == b.dtype and a.shape == b.shape, name
+        assert np.array_equal(a, b), name
+
+
+@pytest.mark.parametrize("kind,n,kw", CASES)
+@pytest.mark.parametrize("method", ["idw", "ls"])
+def test_idw_ls_bit_exact(kind, n, kw, method):
+    I, O = _pair(kind, n, kw)
+    W, nv = I.interpolate("u", method)
+    Wo, nvo = O.interpolate("u", method)
+    assert W.shape == Wo.shape and W.indptr.dtype == np.int32 and W.indices.dtype == np.int32
+    assert np.array_equal(W.indptr, Wo.indptr)
+    assert np.array_equal(W.indices, Wo.indices)
+    assert np.array_equal(W.data, Wo.data, equal_nan=True)
+    assert np.array_equal(nv, nvo)
+
+
+@pytest.mark.parametrize("kind,n,kw", CASES)
+def test_gls_within_tolerance(kind, n, kw):
+    I, O = _pair(kind, n, kw)
+    W, nv = I.interpolate("u", "gls")
+    Wo, nvo = O.interpolate("u", "gls")
+    assert np.array_equal(W.indptr, Wo.indptr)
+    assert np.array_equal(W.indices, Wo.indices)
+    assert np.array_equal(np.isnan(W.data), np.isnan(Wo.data))
+    assert gls_errors(W, Wo) <= GLS_TOL
+    scale = max(1.0, float(np.max(np.abs(nvo))))
+    assert np.max(np.abs(nv - nvo)) <= GLS_TOL * scale
+
+
+def test_gls_small_spacing_tolerance():
+    """cond(M) grows like 1/h: the 50M-tet mesh has h = 0.005."""
+    import ninpol_b200
+    import oracle
+    from ninpol_b200 import meshgen
+    mesh = meshgen.make_case("tet", 8)
+    mesh.points = mesh.points * 0.04
+    I = ninpol_b200.Interpolator()
+    I.load_mesh(mesh_obj=mesh)
+    O = oracle.OracleInterpolator().load_mesh(mesh)
+    W, nv = I.interpolate("u", "gls")
+    Wo, nvo = O.interpolate("u", "gls")
+    assert np.array_equal(W.indices, Wo.indices)
+    assert gls_errors(W, Wo) <= GLS_TOL
+
+
+def test_row_sums_and_linear_exactness():
+    """Size-independent properties: processed rows sum to 1; LS and GLS with
+    homogeneous K reproduce a linear field at interior nodes."""
+    import ninpol_b200
+    from ninpol_b200 import meshgen
+    mesh = meshgen.make_case("tet", 16)
+    K = np.array([[1.0, 0.5, 0.0], [0.5, 1.0, 0.5], [0.0, 0.5, 1.0]]).reshape(1, 9)
+    mesh.cell_data["permeability"] = [np.repeat(K, len(b), axis=0) for b in mesh.cells]
+    I = ninpol_b200.Interpolator()
+    I.load_mesh(mesh_obj=mesh)
+    u = np.concatenate([c for c in mesh.cell_data["u"]])
+    interior = np.asarray(I.grid.boundary_points) == 0
+    exact = mesh.points.sum(axis=1)
+    for method in ("ls", "gls"):
+        W, _ = I.interpolate("u", method)
+        rs = np.asarray(W.sum(axis=1)).ravel()
+        assert np.allclose(rs[interior], 1.0, atol=1e-12)
+        err = np.abs(W.dot(u) - exact)[interior].max()
+        assert err < 1e-12, (method, err)
+
+
+def test_errors_match_reference_conventions():
+    import ninpol_b200
+    from ninpol_b200 import meshgen
+    I = ninpol_b200.Interpolator()
+    with pytest.raises(ValueError):
+        I.load_mesh()
+    with pytest.raises(ValueError, match="Grid not initialized"):
+        I.interpolate("u", "idw")
+    mesh = meshgen.make_case("tet", 3)
+    I.load_mesh(mesh_obj=mesh)
+    with pytest.raises(ValueError, match="not supported"):
+        I.interpolate("u", "lpew3")
+    with pytest.raises(ValueError, match="not found in cells data"):
+        I.interpolate("nope", "idw")
+    with pytest.raises(ValueError, match="more than one dimension"):
+        I.interpolate("permeability", "idw")
+    with pytest.raises(ValueError):
+        I.interpolate("u", "idw", target_points=np.arange(5, dtype=np.int64))
+    del mesh.point_data["neumann_flag_u"]
+    I2 = ninpol_b200.Interpolator()
+    I2.load_mesh(mesh_obj=mesh)
+    with pytest.raises(KeyError):
+        I2.interpolate("u", "ls")
+    assert list(I.supported_methods) == ["gls", "idw", "ls"]
+    W, nv = I.interpolate("u", "idw", target_points=np.arange(I.grid.n_points, dtype=np.int64))
+    assert W.shape == (I.grid.n_points, I.grid.n_elems)
