@@ -118,6 +118,13 @@ int npb_measure_copy_bw(npb_ctx *ctx, int64_t bytes, double *gbs);
 /* Writes `bytes` of device memory (an L2 flush between timed iterations). */
 int npb_flush_l2(npb_ctx *ctx, int64_t bytes);
 int npb_synchronize(npb_ctx *ctx);
+/* CUDA-event stopwatch on the context's stream: start records an event, stop records a second one,
+ * waits for it and returns the elapsed device time between the two in ms. */
+int npb_timer_start(npb_ctx *ctx);
+int npb_timer_stop(npb_ctx *ctx, double *ms);
+/* Page-locked host memory for the CSR outputs / field inputs (full-rate PCIe copies). */
+int npb_host_alloc(int64_t bytes, void **ptr);
+int npb_host_free(void *ptr);
 
 #ifdef __cplusplus
 }

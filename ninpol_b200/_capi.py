@@ -37,6 +37,10 @@ _SIGNATURES = {
     "npb_measure_copy_bw": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_double)]),
     "npb_flush_l2": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64]),
     "npb_synchronize": (ctypes.c_int, [ctypes.c_void_p]),
+    "npb_timer_start": (ctypes.c_int, [ctypes.c_void_p]),
+    "npb_timer_stop": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),
+    "npb_host_alloc": (ctypes.c_int, [ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p)]),
+    "npb_host_free": (ctypes.c_int, [ctypes.c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -183,3 +187,38 @@ class Context:
 
     def synchronize(self):
         check(self.lib.npb_synchronize(self.handle))
+
+    def timer_start(self):
+        check(self.lib.npb_timer_start(self.handle))
+
+    def timer_stop(self):
+        v = ctypes.c_double(0.0)
+        check(self.lib.npb_timer_stop(self.handle, ctypes.byref(v)))
+        return float(v.value)
+
+
+class _PinnedOwner:
+    """Owns one cudaHostAlloc block; numpy arrays made from it keep it alive through `.base`."""
+
+    def __init__(self, nbytes, shape, dtype):
+        self.lib = load_library()
+        self.ptr = ctypes.c_void_p()
+        check(self.lib.npb_host_alloc(int(nbytes), ctypes.byref(self.ptr)))
+        self.__array_interface__ = {"shape": tuple(shape), "typestr": np.dtype(dtype).str,
+                                    "data": (self.ptr.value, False), "version": 3}
+
+    def __del__(self):
+        try:
+            if self.ptr and self.ptr.value:
+                self.lib.npb_host_free(self.ptr)
+                self.ptr = ctypes.c_void_p()
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype):
+    """numpy array in page-locked host memory (full-rate PCIe copies); freed when the last view dies."""
+    shape = (int(shape),) if np.ndim(shape) == 0 else tuple(int(x) for x in shape)
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    return np.asarray(_PinnedOwner(max(n, 1) * dtype.itemsize, shape, dtype))

@@ -133,6 +133,8 @@ extern "C" int npb_destroy(npb_ctx *c)
     if (c->scratch) cudaFree(c->scratch);
     if (c->gls_ws) cudaFree(c->gls_ws);
     if (c->counters) cudaFree(c->counters);
+    if (c->ev_a) cudaEventDestroy(c->ev_a);
+    if (c->ev_b) cudaEventDestroy(c->ev_b);
     cudaStreamDestroy(c->stream);
     delete c;
     return NPB_OK;
@@ -404,6 +406,7 @@ extern "C" int npb_interpolate_count(npb_ctx *c, int method, int64_t *nnz)
         else
             NPB_TRY(npb_k2_idw_ls(c, method, c->lo, c->hi));
         tm.stop();
+        if (method != NPB_METHOD_GLS) c->timings["k2_main"] = c->timings["k2"];
     }
     {
         NpbTimer tm(c, "k3_count");
@@ -480,6 +483,43 @@ extern "C" int npb_timing(npb_ctx *c, const char *name, double *ms)
         return NPB_ERR_ARG;
     }
     *ms = it->second;
+    return NPB_OK;
+}
+
+extern "C" int npb_timer_start(npb_ctx *c)
+{
+    if (!c) return NPB_ERR_ARG;
+    NPB_CUDA(cudaSetDevice(c->device));
+    if (!c->ev_a) {
+        NPB_CUDA(cudaEventCreate(&c->ev_a));
+        NPB_CUDA(cudaEventCreate(&c->ev_b));
+    }
+    NPB_CUDA(cudaEventRecord(c->ev_a, c->stream));
+    return NPB_OK;
+}
+
+extern "C" int npb_timer_stop(npb_ctx *c, double *ms)
+{
+    if (!c || !ms || !c->ev_a) return NPB_ERR_ARG;
+    NPB_CUDA(cudaEventRecord(c->ev_b, c->stream));
+    NPB_CUDA(cudaEventSynchronize(c->ev_b));
+    float f = 0.f;
+    NPB_CUDA(cudaEventElapsedTime(&f, c->ev_a, c->ev_b));
+    *ms = f;
+    return NPB_OK;
+}
+
+extern "C" int npb_host_alloc(int64_t bytes, void **ptr)
+{
+    if (!ptr || bytes < 0) return NPB_ERR_ARG;
+    *ptr = nullptr;
+    NPB_CUDA(cudaHostAlloc(ptr, (size_t)(bytes > 0 ? bytes : 8), cudaHostAllocDefault));
+    return NPB_OK;
+}
+
+extern "C" int npb_host_free(void *ptr)
+{
+    if (ptr) NPB_CUDA(cudaFreeHost(ptr));
     return NPB_OK;
 }
 

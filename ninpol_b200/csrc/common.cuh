@@ -113,6 +113,7 @@ struct npb_ctx {
     void *gls_ws = nullptr;
     size_t gls_ws_cap = 0;
     int *counters = nullptr;     // small device int array (work counters, flags)
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;  // npb_timer_start / stop
 };
 
 // ---- helpers implemented in capi.cu ----

@@ -4,43 +4,57 @@
 // (:234-249), build_ls_matrices (:252-356), set_neumann_rows (:374-416), solve_ls (:420-474, LAPACK
 // DGELS on an (E+3F+B) x (3E+1) system with E right-hand sides, keeping only the last row of X).
 //
-// Algebra: with M = [A | c] (A = first 3E columns, c = last column = 1 on the E element
-// rows, 0 elsewhere) and r = c - A argmin_g |A g - c| the residual of ONE least-squares problem,
+// Algebra: with M = [A | c] (A = the 3E gradient columns, c = last column = 1 on the E
+// element rows, 0 elsewhere) and r = c - A argmin_g |A g - c| the residual of ONE least-squares problem,
 //     weights_i = X[3E, i] = r_i / |r|^2 = r_i / sum_j r_j          (i < E),
-// so one Householder QR of A with the single right-hand side c replaces the reference's E solves.
-// The all-zero rows the reference leaves for boundary faces (gls.pyx:340-344) do not change a
-// least-squares solution and are not materialised.  Reproduced reference behaviour: Q3 (neumann[p] is
-// the weight of the node's LAST element, not the Neumann term; the Neumann right-hand side is dead),
-// Q4 (that value is added to every weight of the row), Q8 (all faces boundary -> zero row).
+// so one QR of A with the single right-hand side c replaces the reference's E solves.  The all-zero
+// rows the reference leaves for boundary faces (gls.pyx:340-344) do not change a least-squares
+// solution and are not materialised.  Reproduced reference behaviour: Q3 (neumann[p] is the weight of
+// the node's LAST element; the Neumann right-hand side is dead), Q4 (that value is added to every
+// weight of the row), Q8 (all faces boundary -> zero row).
 //
-// Mapping: one warp per node, the dense system lives in shared memory (row-major, lanes over columns,
-// loops over rows), nodes are bucketed by workspace size so small stars (hex, boundary) get many
-// resident warps and large stars fall back to a global-memory workspace.  FP64-FMA bound, not HBM
-// bound.
-#include "common.cuh"
+// Structure exploited: A is block sparse — 3 columns per element; an element row touches one block, the
+// 3 rows of an interior face touch the two blocks of its elements, a Neumann row touches one block.
+// The kernel runs a MULTIFRONTAL Householder QR per node: element blocks are eliminated in greedy
+// minimum-degree order (adjacency kept as per-lane bitmasks); eliminating block i gathers the row
+// groups that contain i into a small dense front (rows x (3*|blocks|+1)), applies 3 Householder
+// reflections, keeps the 3 pivot rows as rows of R and leaves the remaining rows as one new group.
+// An interior node of the 50M-tet mesh (E=24, F=36) costs ~0.11 MFLOP this way instead of 1.19 MFLOP
+// for a dense one-RHS QR (1.94 MFLOP in the reference).  Back substitution through the stored R rows
+// gives g, then r_i = 1 - d_i . g_i on the element rows.
+//
+// Mapping: one warp per node; fronts, row groups and R live in a per-warp shared-memory arena with
+// in-place compaction; lanes run over front columns, loops over front rows.  Nodes are bucketed by
+// star size so small stars get many resident warps; stars that do not fit (E > 64, arena overflow) go
+// to the dense global-memory kernel of k2_gls_dense.cu.  FP64-FMA / shared-memory bound, not HBM bound
+// (SURVEY.md Q13).
+#include "gls_common.cuh"
 
-#define GLS_NCLASS 6
-// workspace caps (bytes) of classes 1..4; class 5 = global-memory workspace; class 0 = skipped node
-__constant__ int c_gls_cap[GLS_NCLASS] = {0, 12 * 1024, 40 * 1024, 80 * 1024, 112 * 1024, 0};
-static const int h_gls_cap[GLS_NCLASS] = {0, 12 * 1024, 40 * 1024, 80 * 1024, 112 * 1024, 0};
+typedef unsigned long long u64;
 
-struct GlsArgs {
-    const int32_t *esup_ptr, *esup, *fsup_ptr, *fsup;
-    const int2 *esuf2;
-    const uint8_t *bpoint, *nflag;
-    const double *coords, *cent, *fcent, *fnormal, *perm, *diff_mag;
-    double *wbuf;
-    int32_t *rowcnt;
-    double *neumann;
-    i64 wbase;
+#define MF_NCLASS 8          // 0 = skipped node, 1..6 = shared-memory classes, 7 = dense fallback
+#define MF_SCAP 64           // max row groups merged into one front
+
+struct MfClass {
+    int acap;   // arena capacity (doubles)
+    int ecap;   // max elements around the node
+    int fcap;   // max faces around the node
 };
+__constant__ MfClass c_mf[MF_NCLASS] = {{0, 0, 0},        {1536, 12, 20},  {2560, 16, 28},  {4224, 24, 40},
+                                        {6144, 32, 56},   {9216, 48, 80},  {13312, 64, 112}, {0, 0, 0}};
+static const MfClass h_mf[MF_NCLASS] = {{0, 0, 0},        {1536, 12, 20},  {2560, 16, 28},  {4224, 24, 40},
+                                        {6144, 32, 56},   {9216, 48, 80},  {13312, 64, 112}, {0, 0, 0}};
 
-__host__ __device__ __forceinline__ size_t gls_ws_bytes(int E, int m)
+__host__ __device__ __forceinline__ int mf_ngcap(const MfClass &k) { return k.ecap + k.fcap + 2 * k.ecap; }
+__host__ __device__ __forceinline__ int mf_mcap(const MfClass &k) { int m = k.ecap + 4 * k.fcap; return m < 96 ? m : 96; }
+__host__ __device__ __forceinline__ size_t mf_smem_bytes(const MfClass &k)
 {
-    // M [m, 3E+1] + vv [m] + rinv/g [3E+1] doubles, then es [E] ints (padded to 8 bytes)
-    size_t d = (size_t)m * (3 * E + 1) + m + (3 * E + 1);
-    return d * 8 + (((size_t)E * 4 + 7) & ~(size_t)7);
+    size_t d = (size_t)k.acap + 4 * (size_t)mf_mcap(k) + 6 * (size_t)k.ecap;  // arena, vbuf[.][4], gvec, dvec
+    size_t b = d * 8 + (size_t)mf_ngcap(k) * (8 + 4 + 2 + 1 + 1 + 1 + 1);   // group table
+    b += (size_t)k.ecap * 4 + MF_SCAP * 4 + 64;                             // es, S list, colblk
+    return (b + 15) & ~(size_t)15;
 }
+__host__ __device__ __forceinline__ int mf_arena_need(int E, int m) { return 30 * m + 4 * E + 128; }
 
 // per node: Dirichlet / Q8 nodes are finished here (zero row); the others get a size class
 __global__ void k_gls_classify(GlsArgs a, i64 lo, i64 hi, uint8_t *__restrict__ cls)
@@ -66,63 +80,137 @@ __global__ void k_gls_classify(GlsArgs a, i64 lo, i64 hi, uint8_t *__restrict__ 
         return;
     }
     int m = E + 3 * (F - nb) + (neu ? nb : 0);
-    size_t need = gls_ws_bytes(E, m);
-    int k = GLS_NCLASS - 1;
-    for (int q = 1; q < GLS_NCLASS - 1; q++)
-        if (need <= (size_t)c_gls_cap[q]) {
+    int need = mf_arena_need(E, m);
+    int k = MF_NCLASS - 1;
+    for (int q = 1; q < MF_NCLASS - 1; q++)
+        if (E <= c_mf[q].ecap && F <= c_mf[q].fcap && need <= c_mf[q].acap) {
             k = q;
             break;
         }
     cls[p] = (uint8_t)k;
 }
 
-__device__ __forceinline__ double warp_sum(double v)
+__device__ __forceinline__ u64 warp_or64(u64 v)
 {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+    unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
+    unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
+    return ((u64)hi << 32) | lo;
+}
+__device__ __forceinline__ int nth_set_bit(u64 m, int n)  // index of the n-th (0-based) set bit
+{
+    for (int q = 0; q < n; q++) m &= m - 1;
+    return __ffsll((long long)m) - 1;
 }
 
-// One warp per node.  ws = workspace of this warp (shared or global), generic address space.
-__device__ void gls_node(const GlsArgs &a, int p, double *ws)
+struct MfWs {
+    double *arena, *vbuf, *gvec, *dvec;
+    u64 *g_mask;
+    int *g_off;
+    unsigned short *g_nr;
+    unsigned char *g_ld, *g_kind, *g_piv;
+    int *es;
+    int *s_list;            // packed (gid | rowbase << 16)
+    unsigned char *colblk;  // block id of every 3-column slot of the current front
+};
+
+__device__ __forceinline__ MfWs mf_carve(unsigned char *base, const MfClass &k)
+{
+    MfWs w;
+    int ng = mf_ngcap(k);
+    w.arena = (double *)base;
+    w.vbuf = w.arena + k.acap;                  // [mcap][4]: the three Householder vectors of a front
+    w.gvec = w.vbuf + 4 * mf_mcap(k);
+    w.dvec = w.gvec + 3 * k.ecap;
+    w.g_mask = (u64 *)(w.dvec + 3 * k.ecap);
+    w.g_off = (int *)(w.g_mask + ng);
+    w.es = w.g_off + ng;
+    w.s_list = w.es + k.ecap;
+    w.g_nr = (unsigned short *)(w.s_list + MF_SCAP);
+    w.g_ld = (unsigned char *)(w.g_nr + ng);
+    w.g_kind = w.g_ld + ng;
+    w.g_piv = w.g_kind + ng;
+    w.colblk = w.g_piv + ng;                    // [64]
+    return w;
+}
+
+// Slides every live table entry down to close the holes left by consumed groups.  Table order equals
+// arena order (entries are only ever appended at the arena top), so a forward pass is a safe memmove.
+__device__ int mf_compact(MfWs &w, int ng, int lane)
+{
+    int top = 0;
+    for (int g = 0; g < ng; g++) {
+        int nr = w.g_nr[g];
+        if (nr == 0) continue;
+        int sz = nr * (int)w.g_ld[g];
+        int src = w.g_off[g];
+        if (src != top) {
+            for (int i0 = 0; i0 < sz; i0 += 32) {
+                int i = i0 + lane;
+                double v = 0.0;
+                if (i < sz) v = w.arena[src + i];
+                __syncwarp();
+                if (i < sz) w.arena[top + i] = v;
+                __syncwarp();
+            }
+            if (lane == 0) w.g_off[g] = top;
+        }
+        top += sz;
+    }
+    __syncwarp();
+    return top;
+}
+
+#define MF_RPL 3   // front rows per lane in the panel factorisation: fronts of up to 96 rows
+
+__device__ __forceinline__ void hh_scalars(double sigma, double x0, double &alpha, double &beta)
+{
+    if (sigma == 0.0) {
+        alpha = 0.0;
+        beta = 0.0;
+        return;
+    }
+    double sq = sqrt(sigma);
+    alpha = (x0 >= 0.0) ? -sq : sq;
+    beta = 1.0 / (sigma - x0 * alpha);
+}
+
+// returns 0 on success, 1 when the star does not fit this class (caller reroutes it to the dense kernel)
+__device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfClass &kc)
 {
     const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    MfWs w = mf_carve(smem, kc);
     const int eb = a.esup_ptr[p], E = a.esup_ptr[p + 1] - eb;
     const int fb = a.fsup_ptr[p], F = a.fsup_ptr[p + 1] - fb;
     const bool neu = a.nflag[p] != 0;
-    const int n = 3 * E, ld = n + 1;
     const double xv0 = a.coords[(i64)p * 3 + 0], xv1 = a.coords[(i64)p * 3 + 1], xv2 = a.coords[(i64)p * 3 + 2];
+    const int ngcap = mf_ngcap(kc);
 
-    // ---- pass 0: count interior / boundary faces ----
+    // ---- setup: esup row, element groups ----
+    for (int i = lane; i < E; i += 32) w.es[i] = a.esup[eb + i];
+    __syncwarp();
+    for (int i = lane; i < E; i += 32) {
+        const double *cc = a.cent + (i64)w.es[i] * 3;
+        double d0 = cc[0] - xv0, d1 = cc[1] - xv1, d2 = cc[2] - xv2;
+        w.dvec[3 * i] = d0; w.dvec[3 * i + 1] = d1; w.dvec[3 * i + 2] = d2;
+        double *row = w.arena + 4 * i;                    // [ d^T | 1 ]   gls.pyx:268-281
+        row[0] = d0; row[1] = d1; row[2] = d2; row[3] = 1.0;
+        w.g_mask[i] = 1ull << i;
+        w.g_off[i] = 4 * i;
+        w.g_nr[i] = 1;
+        w.g_ld[i] = 4;
+        w.g_kind[i] = 0;
+    }
+    // ---- face groups (gls.pyx:291-356) and Neumann groups (:394-416) ----
     int n_if = 0;
     for (int f0 = 0; f0 < F; f0 += 32) {
         int fi = f0 + lane;
         bool interior = false;
         if (fi < F) interior = a.esuf2[a.fsup[fb + fi]].y >= 0;
-        n_if += __popc(__ballot_sync(0xffffffffu, interior));
+        n_if += __popc(__ballot_sync(FULL, interior));
     }
     const int n_bf = F - n_if;
-    const int m = E + 3 * n_if + (neu ? n_bf : 0);
-
-    double *M = ws;
-    double *vv = M + (size_t)m * ld;
-    double *gg = vv + m;             // [ld]: reciprocal diagonal, then the solution g
-    int *es = (int *)(gg + ld);      // [E]: the node's esup row
-
-    for (int i = lane; i < m * ld; i += 32) M[i] = 0.0;
-    for (int i = lane; i < E; i += 32) es[i] = a.esup[eb + i];
-    __syncwarp();
-
-    // ---- element rows (gls.pyx:268-281): [ (x_K - x_v)^T at block i | 1 ] ----
-    for (int i = lane; i < E; i += 32) {
-        const double *cc = a.cent + (i64)es[i] * 3;
-        double *row = M + (size_t)i * ld;
-        row[3 * i + 0] = cc[0] - xv0;
-        row[3 * i + 1] = cc[1] - xv1;
-        row[3 * i + 2] = cc[2] - xv2;
-        row[n] = 1.0;
-    }
-    // ---- face rows (gls.pyx:291-356) and Neumann rows (:394-416) ----
+    const int off_if = 4 * E, off_bf = 4 * E + 21 * n_if;
     int if_seen = 0, bf_seen = 0;
     for (int f0 = 0; f0 < F; f0 += 32) {
         int fi = f0 + lane;
@@ -134,148 +222,392 @@ __device__ void gls_node(const GlsArgs &a, int p, double *ws)
         }
         bool interior = (fi < F) && e2.y >= 0;
         bool boundary = (fi < F) && e2.y < 0;
-        unsigned mi = __ballot_sync(0xffffffffu, interior);
-        unsigned mb = __ballot_sync(0xffffffffu, boundary);
+        unsigned mi = __ballot_sync(FULL, interior);
+        unsigned mb = __ballot_sync(FULL, boundary);
         unsigned below = (1u << lane) - 1u;
         if (interior) {
             int j = if_seen + __popc(mi & below);
             int I1 = 0, I2 = 0;
             for (int k = 0; k < E; k++) {
-                int ek = es[k];
+                int ek = w.es[k];
                 if (ek == e2.x) I1 = k;
                 if (ek == e2.y) I2 = k;
             }
             const double *Nn = a.fnormal + (i64)face * 3;
             const double *xs = a.fcent + (i64)face * 3;
             double N0 = Nn[0], N1 = Nn[1], N2 = Nn[2];
-            double t0 = xv0 - xs[0], t1 = xv1 - xs[1], t2 = xv2 - xs[2];   // T1 = x_v - x_S
-            double c0 = N1 * t2 - N2 * t1, c1 = N2 * t0 - N0 * t2, c2 = N0 * t1 - N1 * t0;  // T2 = N x T1
+            double t0 = xv0 - xs[0], t1 = xv1 - xs[1], t2 = xv2 - xs[2];                     // T1 = x_v - x_S
+            double c0 = N1 * t2 - N2 * t1, c1 = N2 * t0 - N0 * t2, c2 = N0 * t1 - N1 * t0;    // T2 = N x T1
             double eta = fmax(fmax(0.0, a.diff_mag[e2.x]), a.diff_mag[e2.y]);
             double tau = pow(sqrt(c0 * c0 + c1 * c1 + c2 * c2), -eta);
             const double *K1 = a.perm + (i64)e2.x * 9;
             const double *K2 = a.perm + (i64)e2.y * 9;
-            double *r1 = M + (size_t)(E + 3 * j) * ld;
-            double *r2 = r1 + ld;
-            double *r3 = r2 + ld;
+            // columns in ascending block order: the owner (smaller element id) has the smaller local index
+            double s1 = -1.0, s2 = 1.0;
+            int lo_i = I1, hi_i = I2;
+            if (I2 < I1) { lo_i = I2; hi_i = I1; s1 = 1.0; s2 = -1.0; const double *t = K1; K1 = K2; K2 = t; }
+            double *r1 = w.arena + off_if + 21 * j;   // 3 rows x (3 + 3 + rhs)
+            double *r2 = r1 + 7, *r3 = r2 + 7;
 #pragma unroll
             for (int q = 0; q < 3; q++) {
-                double k1n = K1[3 * q] * N0 + K1[3 * q + 1] * N1 + K1[3 * q + 2] * N2;
-                double k2n = K2[3 * q] * N0 + K2[3 * q + 1] * N1 + K2[3 * q + 2] * N2;
-                r1[3 * I1 + q] = -k1n;
-                r1[3 * I2 + q] = k2n;
+                r1[q] = s1 * (K1[3 * q] * N0 + K1[3 * q + 1] * N1 + K1[3 * q + 2] * N2);
+                r1[3 + q] = s2 * (K2[3 * q] * N0 + K2[3 * q + 1] * N1 + K2[3 * q + 2] * N2);
             }
-            r2[3 * I1 + 0] = -t0; r2[3 * I1 + 1] = -t1; r2[3 * I1 + 2] = -t2;
-            r2[3 * I2 + 0] = t0;  r2[3 * I2 + 1] = t1;  r2[3 * I2 + 2] = t2;
-            r3[3 * I1 + 0] = -(tau * c0); r3[3 * I1 + 1] = -(tau * c1); r3[3 * I1 + 2] = -(tau * c2);
-            r3[3 * I2 + 0] = tau * c0;    r3[3 * I2 + 1] = tau * c1;    r3[3 * I2 + 2] = tau * c2;
+            r2[0] = s1 * t0; r2[1] = s1 * t1; r2[2] = s1 * t2; r2[3] = s2 * t0; r2[4] = s2 * t1; r2[5] = s2 * t2;
+            r3[0] = s1 * (tau * c0); r3[1] = s1 * (tau * c1); r3[2] = s1 * (tau * c2);
+            r3[3] = s2 * (tau * c0); r3[4] = s2 * (tau * c1); r3[5] = s2 * (tau * c2);
+            r1[6] = 0.0; r2[6] = 0.0; r3[6] = 0.0;
+            int g = E + j;
+            w.g_mask[g] = (1ull << lo_i) | (1ull << hi_i);
+            w.g_off[g] = off_if + 21 * j;
+            w.g_nr[g] = 3;
+            w.g_ld[g] = 7;
+            w.g_kind[g] = 0;
         }
         if (boundary && neu) {
             int j = bf_seen + __popc(mb & below);
             int Ik = 0;
             for (int k = 0; k < E; k++)
-                if (es[k] == e2.x) Ik = k;
+                if (w.es[k] == e2.x) Ik = k;
             const double *Nn = a.fnormal + (i64)face * 3;
             const double *K1 = a.perm + (i64)e2.x * 9;
             double N0 = Nn[0], N1 = Nn[1], N2 = Nn[2];
-            double *rr = M + (size_t)(E + 3 * n_if + j) * ld;
+            double *rr = w.arena + off_bf + 4 * j;
 #pragma unroll
-            for (int q = 0; q < 3; q++) rr[3 * Ik + q] = -(K1[3 * q] * N0 + K1[3 * q + 1] * N1 + K1[3 * q + 2] * N2);
+            for (int q = 0; q < 3; q++) rr[q] = -(K1[3 * q] * N0 + K1[3 * q + 1] * N1 + K1[3 * q + 2] * N2);
+            rr[3] = 0.0;
+            int g = E + n_if + j;
+            w.g_mask[g] = 1ull << Ik;
+            w.g_off[g] = off_bf + 4 * j;
+            w.g_nr[g] = 1;
+            w.g_ld[g] = 4;
+            w.g_kind[g] = 0;
         }
         if_seen += __popc(mi);
         bf_seen += __popc(mb);
     }
+    int ng = E + n_if + (neu ? n_bf : 0);
+    int top = off_bf + (neu ? 4 * n_bf : 0);
     __syncwarp();
 
-    // ---- Householder QR of [A | c], natural column order ----
-    const int kmax = n < m ? n : m;
-    for (int k = 0; k < kmax; k++) {
-        double part = 0.0;
-        for (int r = k + lane; r < m; r += 32) {
-            double x = M[(size_t)r * ld + k];
-            vv[r] = x;
-            part += x * x;
+    // ---- adjacency bitmasks: lane b owns blocks b and b + 32 ----
+    u64 adjA = 0, adjB = 0;
+    {
+        const u64 bitA = 1ull << lane, bitB = 1ull << (lane + 32);
+        for (int g = 0; g < ng; g++) {
+            u64 mk = w.g_mask[g];
+            if (mk & bitA) adjA |= mk;
+            if (mk & bitB) adjB |= mk;
         }
-        double sigma = warp_sum(part);
-        __syncwarp();
-        if (sigma == 0.0) {
-            if (lane == 0) gg[k] = 0.0;
-            continue;
+    }
+    u64 alive = (E >= 64) ? ~0ull : ((1ull << E) - 1ull);
+
+    // ---- elimination ----
+    while (alive) {
+        // (a) minimum-degree pivot block
+        unsigned keyA = ((alive >> lane) & 1ull) ? (unsigned)((__popcll(adjA) << 8) | lane) : 0xffffffffu;
+        unsigned keyB = ((alive >> (lane + 32)) & 1ull) ? (unsigned)((__popcll(adjB) << 8) | (lane + 32)) : 0xffffffffu;
+        unsigned key = __reduce_min_sync(FULL, keyA < keyB ? keyA : keyB);
+        const int piv = (int)(key & 0xffu);
+        const u64 pbit = 1ull << piv;
+        // (b) row groups containing the pivot block
+        int nS = 0, rho = 0;
+        u64 U = 0;
+        for (int g0 = 0; g0 < ng; g0 += 32) {
+            int g = g0 + lane;
+            bool in = false;
+            int nr = 0;
+            u64 mk = 0;
+            if (g < ng) {
+                nr = w.g_nr[g];
+                mk = w.g_mask[g];
+                in = nr > 0 && w.g_kind[g] == 0 && (mk & pbit);
+            }
+            unsigned bal = __ballot_sync(FULL, in);
+            if (bal == 0) continue;
+            int v = in ? nr : 0;   // exclusive prefix of the row counts over the selected lanes
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += t;
+            }
+            int pos = nS + __popc(bal & ((1u << lane) - 1u));
+            if (in && pos < MF_SCAP) w.s_list[pos] = g | ((rho + incl - v) << 16);
+            nS += __popc(bal);
+            rho += __shfl_sync(FULL, incl, 31);
+            U |= warp_or64(in ? mk : 0ull);
         }
-        double x0 = vv[k];
-        double alpha = (x0 >= 0.0) ? -sqrt(sigma) : sqrt(sigma);
-        double beta = 1.0 / (sigma - x0 * alpha);
-        __syncwarp();
-        if (lane == 0) {
-            vv[k] = x0 - alpha;
-            M[(size_t)k * ld + k] = alpha;
-            gg[k] = 1.0 / alpha;
+        if (nS > MF_SCAP || rho > 32 * MF_RPL) return 1;
+        const u64 Up = U & ~pbit;
+        const int nblk = __popcll(U);
+        const int c = 3 * nblk + 1;
+        const int need = rho * c;
+        // (c) room for the front at the arena top
+        if (top + need > kc.acap) {
+            top = mf_compact(w, ng, lane);
+            if (top + need > kc.acap) return 1;
         }
+        if (ng + 2 > ngcap || rho > mf_mcap(kc)) return 1;
+        // block id of every column slot: slot 0 = pivot, then the other blocks ascending
+        if ((Up >> lane) & 1ull) w.colblk[1 + __popcll(Up & ((1ull << lane) - 1ull))] = (unsigned char)lane;
+        if ((Up >> (lane + 32)) & 1ull) w.colblk[1 + __popcll(Up & ((1ull << (lane + 32)) - 1ull))] = (unsigned char)(lane + 32);
+        if (lane == 0) w.colblk[0] = (unsigned char)piv;
         __syncwarp();
-        for (int j0 = k + 1; j0 < ld; j0 += 32) {
+        double *Fm = w.arena + top;
+        // (d) assemble: lanes over front columns [pivot block | other blocks ascending | rhs]
+        for (int j0 = 0; j0 < c; j0 += 32) {
             int j = j0 + lane;
-            if (j < ld) {
-                double s0 = 0.0, s1 = 0.0;
-                int r = k;
-                for (; r + 1 < m; r += 2) {
-                    s0 += vv[r] * M[(size_t)r * ld + j];
-                    s1 += vv[r + 1] * M[(size_t)(r + 1) * ld + j];
+            if (j >= c) continue;
+            const bool is_rhs = (j == c - 1);
+            const int blk = is_rhs ? 0 : w.colblk[j / 3];
+            const int comp = j % 3;
+            const u64 below = (1ull << blk) - 1ull;
+            for (int t = 0; t < nS; t++) {
+                int packed = w.s_list[t];
+                int g = packed & 0xffff;
+                u64 mk = w.g_mask[g];
+                int nr = w.g_nr[g], ld = w.g_ld[g];
+                bool has = is_rhs || ((mk >> blk) & 1ull);
+                int sc = is_rhs ? 3 * __popcll(mk) : 3 * __popcll(mk & below) + comp;
+                const double *src = w.arena + w.g_off[g] + sc;
+                double *dst = Fm + (packed >> 16) * c + j;
+                for (int r = 0; r < nr; r++) {
+                    *dst = has ? *src : 0.0;
+                    src += ld;
+                    dst += c;
                 }
-                if (r < m) s0 += vv[r] * M[(size_t)r * ld + j];
-                double s = (s0 + s1) * beta;
-                for (r = k; r < m; r++) M[(size_t)r * ld + j] -= s * vv[r];
             }
         }
         __syncwarp();
-    }
-    // ---- back substitution R g = z (column oriented; z lives in column n) ----
-    for (int k = kmax - 1; k >= 0; k--) {
-        double gk = M[(size_t)k * ld + n] * gg[k];
+        for (int t = lane; t < nS; t += 32) w.g_nr[w.s_list[t] & 0xffff] = 0;   // consumed
+        // (e) panel: Householder on the three pivot columns, lanes over rows, entries in registers
+        double a0[MF_RPL], a1[MF_RPL], a2[MF_RPL];
+#pragma unroll
+        for (int q = 0; q < MF_RPL; q++) {
+            int r = lane + 32 * q;
+            bool ok = r < rho;
+            a0[q] = ok ? Fm[r * c + 0] : 0.0;
+            a1[q] = ok ? Fm[r * c + 1] : 0.0;
+            a2[q] = ok ? Fm[r * c + 2] : 0.0;
+        }
+        double alpha0, beta0, alpha1, beta1, alpha2, beta2, d10, d20, d21;
+        {
+            double sg = 0.0;
+#pragma unroll
+            for (int q = 0; q < MF_RPL; q++) sg += a0[q] * a0[q];
+            sg = warp_sum(sg);
+            double x00 = __shfl_sync(FULL, a0[0], 0);
+            hh_scalars(sg, x00, alpha0, beta0);
+            if (lane == 0) a0[0] = x00 - alpha0;                  // a0 now holds v0
+            double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+            for (int q = 0; q < MF_RPL; q++) { t1 += a0[q] * a1[q]; t2 += a0[q] * a2[q]; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { t1 += __shfl_xor_sync(FULL, t1, o); t2 += __shfl_xor_sync(FULL, t2, o); }
+            t1 *= beta0; t2 *= beta0;
+#pragma unroll
+            for (int q = 0; q < MF_RPL; q++) { a1[q] -= t1 * a0[q]; a2[q] -= t2 * a0[q]; }
+        }
+        double r01 = __shfl_sync(FULL, a1[0], 0), r02 = __shfl_sync(FULL, a2[0], 0);
+        {
+            if (lane == 0) a1[0] = 0.0;                           // rows above the pivot do not take part
+            double sg = 0.0;
+#pragma unroll
+            for (int q = 0; q < MF_RPL; q++) sg += a1[q] * a1[q];
+            sg = warp_sum(sg);
+            double x11 = __shfl_sync(FULL, a1[0], 1);
+            hh_scalars(sg, x11, alpha1, beta1);
+            if (lane == 1) a1[0] = x11 - alpha1;                  // a1 now holds v1
+            if (lane == 0) a2[0] = 0.0;
+            double t2 = 0.0;
+#pragma unroll
+            for (int q = 0; q < MF_RPL; q++) t2 += a1[q] * a2[q];
+            t2 = warp_sum(t2) * beta1;
+#pragma unroll
+            for (int q = 0; q < MF_RPL; q++) a2[q] -= t2 * a1[q];
+        }
+        double r12 = __shfl_sync(FULL, a2[0], 1);
+        {
+            if (lane == 1) a2[0] = 0.0;
+            double sg = 0.0;
+#pragma unroll
+            for (int q = 0; q < MF_RPL; q++) sg += a2[q] * a2[q];
+            sg = warp_sum(sg);
+            double x22 = __shfl_sync(FULL, a2[0], 2);
+            hh_scalars(sg, x22, alpha2, beta2);
+            if (lane == 2) a2[0] = x22 - alpha2;                  // a2 now holds v2
+            d10 = 0.0; d20 = 0.0; d21 = 0.0;
+#pragma unroll
+            for (int q = 0; q < MF_RPL; q++) { d10 += a1[q] * a0[q]; d20 += a2[q] * a0[q]; d21 += a2[q] * a1[q]; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                d10 += __shfl_xor_sync(FULL, d10, o);
+                d20 += __shfl_xor_sync(FULL, d20, o);
+                d21 += __shfl_xor_sync(FULL, d21, o);
+            }
+        }
+        // v vectors to shared memory as [row][4]; the pivot rows' panel entries of R
+#pragma unroll
+        for (int q = 0; q < MF_RPL; q++) {
+            int r = lane + 32 * q;
+            if (r < rho) {
+                double2 *vp = reinterpret_cast<double2 *>(w.vbuf + 4 * r);
+                vp[0] = make_double2(a0[q], a1[q]);
+                vp[1] = make_double2(a2[q], 0.0);
+            }
+        }
+        if (lane == 0) {
+            Fm[0] = alpha0; Fm[1] = r01; Fm[2] = r02;
+            if (rho > 1) { Fm[c + 1] = alpha1; Fm[c + 2] = r12; }
+            if (rho > 2) Fm[2 * c + 2] = alpha2;
+        }
         __syncwarp();
-        if (lane == 0) gg[k] = gk;
-        for (int r = lane; r < k; r += 32) M[(size_t)r * ld + n] -= M[(size_t)r * ld + k] * gk;
+        // (f) apply the three reflections to the other columns: two passes over the rows
+        for (int j0 = 3; j0 < c; j0 += 32) {
+            int j = j0 + lane;
+            if (j >= c) continue;
+            double w0 = 0.0, w1 = 0.0, w2 = 0.0;
+            {
+                const double *fp = Fm + j;
+                const double2 *vp = reinterpret_cast<const double2 *>(w.vbuf);
+#pragma unroll 4
+                for (int r = 0; r < rho; r++) {
+                    double f = *fp;
+                    double2 va = vp[0], vb = vp[1];
+                    w0 += va.x * f; w1 += va.y * f; w2 += vb.x * f;
+                    fp += c; vp += 2;
+                }
+            }
+            double s0 = beta0 * w0;
+            double s1 = beta1 * (w1 - d10 * s0);
+            double s2 = beta2 * (w2 - d20 * s0 - d21 * s1);
+            {
+                double *fp = Fm + j;
+                const double2 *vp = reinterpret_cast<const double2 *>(w.vbuf);
+#pragma unroll 4
+                for (int r = 0; r < rho; r++) {
+                    double2 va = vp[0], vb = vp[1];
+                    *fp = *fp - (va.x * s0 + va.y * s1 + vb.x * s2);
+                    fp += c; vp += 2;
+                }
+            }
+        }
+        __syncwarp();
+        // (g) table entries: the pivot rows (rows of R) and the remaining rows as one new group
+        const int npiv = rho < 3 ? rho : 3;
+        const int left = rho - npiv;
+        const bool keep = left > 0 && Up != 0;
+        if (lane == 0) {
+            w.g_mask[ng] = U;
+            w.g_off[ng] = top;
+            w.g_nr[ng] = (unsigned short)npiv;
+            w.g_ld[ng] = (unsigned char)c;
+            w.g_kind[ng] = 1;
+            w.g_piv[ng] = (unsigned char)piv;
+            w.g_mask[ng + 1] = Up;
+            w.g_off[ng + 1] = top + npiv * c + 3;
+            w.g_nr[ng + 1] = (unsigned short)(keep ? left : 0);
+            w.g_ld[ng + 1] = (unsigned char)c;
+            w.g_kind[ng + 1] = 0;
+        }
+        top += keep ? need : npiv * c;
+        ng += 2;
+        // (h) adjacency update: the neighbours of the pivot become a clique
+        if ((Up >> lane) & 1ull) adjA = (adjA | U) & ~pbit;
+        if ((Up >> (lane + 32)) & 1ull) adjB = (adjB | U) & ~pbit;
+        alive &= ~pbit;
         __syncwarp();
     }
-    for (int k = kmax + lane; k < n; k += 32) gg[k] = 0.0;
+
+    // ---- back substitution through the R entries, newest first ----
+    for (int i = lane; i < 3 * E; i += 32) w.gvec[i] = 0.0;
     __syncwarp();
+    for (int g = ng - 2; g >= 0; g--) {
+        if (w.g_kind[g] != 1) continue;
+        const int npiv = w.g_nr[g], c = w.g_ld[g], piv = w.g_piv[g];
+        const u64 Up = w.g_mask[g] & ~(1ull << piv);
+        const double *R = w.arena + w.g_off[g];
+        double p0 = 0.0, p1 = 0.0, p2 = 0.0;
+        for (int j0 = 3; j0 < c - 1; j0 += 32) {
+            int j = j0 + lane;
+            if (j < c - 1) {
+                int blk = nth_set_bit(Up, (j - 3) / 3);
+                double gj = w.gvec[3 * blk + (j - 3) % 3];
+                p0 += R[j] * gj;
+                if (npiv > 1) p1 += R[c + j] * gj;
+                if (npiv > 2) p2 += R[2 * c + j] * gj;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            p0 += __shfl_xor_sync(FULL, p0, o);
+            p1 += __shfl_xor_sync(FULL, p1, o);
+            p2 += __shfl_xor_sync(FULL, p2, o);
+        }
+        if (lane == 0) {
+            double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+            if (npiv > 2) {
+                double d = R[2 * c + 2];
+                g2 = d != 0.0 ? (R[2 * c + c - 1] - p2) / d : 0.0;
+            }
+            if (npiv > 1) {
+                double d = R[c + 1];
+                g1 = d != 0.0 ? (R[c + c - 1] - p1 - R[c + 2] * g2) / d : 0.0;
+            }
+            {
+                double d = R[0];
+                g0 = d != 0.0 ? (R[c - 1] - p0 - R[1] * g1 - R[2] * g2) / d : 0.0;
+            }
+            w.gvec[3 * piv] = g0;
+            w.gvec[3 * piv + 1] = g1;
+            w.gvec[3 * piv + 2] = g2;
+        }
+        __syncwarp();
+    }
     // ---- residual on the element rows, weights, CSR values ----
-    double *w = a.wbuf + ((i64)eb - a.wbase);
+    double *wo = a.wbuf + ((i64)eb - a.wbase);
     double part = 0.0;
     for (int i = lane; i < E; i += 32) {
-        const double *cc = a.cent + (i64)es[i] * 3;
-        double ri = 1.0 - ((cc[0] - xv0) * gg[3 * i] + (cc[1] - xv1) * gg[3 * i + 1] + (cc[2] - xv2) * gg[3 * i + 2]);
-        vv[i] = ri;
+        double ri = 1.0 - (w.dvec[3 * i] * w.gvec[3 * i] + w.dvec[3 * i + 1] * w.gvec[3 * i + 1] + w.dvec[3 * i + 2] * w.gvec[3 * i + 2]);
+        w.vbuf[i] = ri;
         part += ri;
     }
     double tot = warp_sum(part);
     __syncwarp();
-    double nv = neu ? vv[E - 1] / tot : 0.0;   // gls.pyx:470-472 (Q3)
+    double nv = neu ? w.vbuf[E - 1] / tot : 0.0;   // gls.pyx:470-472 (Q3)
     int cnt = 0;
     for (int i = lane; i < E; i += 32) {
-        double v = vv[i] / tot + nv;           // interpolator.pyx:618 (Q4)
-        w[i] = v;
+        double v = w.vbuf[i] / tot + nv;           // interpolator.pyx:618 (Q4)
+        wo[i] = v;
         cnt += (v != 0.0) ? 1 : 0;
     }
-    cnt = (int)warp_sum((double)cnt);
+    cnt = __reduce_add_sync(FULL, cnt);
     if (lane == 0) {
         a.rowcnt[p] = cnt;
         a.neumann[p] = nv;
     }
+    __syncwarp();
+    return 0;
 }
 
-// persistent: one warp per CTA; nodes handed out through an atomic counter
+// persistent: one warp per CTA; nodes handed out through an atomic counter; stars that do not fit are
+// appended to the overflow list for the dense kernel
 __global__ void __launch_bounds__(32)
-k_gls_nodes(GlsArgs a, const int32_t *__restrict__ list, int count, int *__restrict__ counter, double *gws,
-            size_t gws_stride)
+k_gls_mf(GlsArgs a, const int32_t *__restrict__ list, int count, int *__restrict__ counter, int klass,
+         int32_t *__restrict__ overflow, int *__restrict__ n_overflow)
 {
-    extern __shared__ double smem_ws[];
-    double *ws = gws ? (double *)((char *)gws + (size_t)blockIdx.x * gws_stride) : smem_ws;
+    extern __shared__ __align__(16) unsigned char smem_mf[];
+    const MfClass kc = c_mf[klass];
     while (true) {
         int i = 0;
         if (threadIdx.x == 0) i = atomicAdd(counter, 1);
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= count) break;
-        gls_node(a, list[i], ws);
+        int p = list[i];
+        int rc = mf_node(a, p, smem_mf, kc);
         __syncwarp();
+        if (rc != 0 && threadIdx.x == 0) overflow[atomicAdd(n_overflow, 1)] = p;
     }
 }
 
@@ -289,39 +621,52 @@ int npb_k2_gls(npb_ctx *c, i64 lo, i64 hi)
     a.fnormal = c->fnormal; a.perm = c->perm; a.diff_mag = c->diff_mag; a.wbuf = c->wbuf; a.rowcnt = c->rowcnt;
     a.neumann = c->neumann; a.wbase = c->wbase;
     i64 nloc = hi - lo;
-    uint8_t *cls = nullptr;
-    NPB_CUDA(cudaMalloc(&cls, (size_t)c->n_points));
+    if (!c->node_list) {
+        // [0, n): work list of the current class; [n, 2n): overflow list; then n bytes of classes
+        NPB_TRY(npb_alloc(c, (void **)&c->node_list, sizeof(int32_t) * 2 * (size_t)c->n_points + (size_t)c->n_points));
+    }
+    int32_t *list = c->node_list, *overflow = c->node_list + c->n_points;
+    uint8_t *cls = (uint8_t *)(c->node_list + 2 * c->n_points);
+    int *n_overflow = c->counters + 40;
+    NPB_CUDA(cudaMemsetAsync(n_overflow, 0, sizeof(int), s));
     k_gls_classify<<<npb_blocks(nloc, 256), 256, 0, s>>>(a, lo, hi, cls);
     NPB_LAUNCH(c);
-    if (!c->node_list) NPB_TRY(npb_alloc(c, (void **)&c->node_list, sizeof(int32_t) * (size_t)c->n_points));
-    for (int k = 1; k < GLS_NCLASS; k++) {
+    float main_ms = 0.f;
+    static const char *cls_names[MF_NCLASS] = {"", "k2_gls_c1", "k2_gls_c2", "k2_gls_c3", "k2_gls_c4", "k2_gls_c5", "k2_gls_c6", "k2_gls_dense"};
+    for (int k = 1; k < MF_NCLASS; k++) c->timings.erase(cls_names[k]);
+    int n_dense_direct = 0;
+    for (int k = 1; k < MF_NCLASS - 1; k++) {
         int count = 0;
-        NPB_TRY(npb_select_class(c, cls, lo, hi, k, c->node_list, &count));
+        NPB_TRY(npb_select_class(c, cls, lo, hi, k, list, &count));
         if (count == 0) continue;
         int *counter = c->counters + 20 + k;
         NPB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), s));
-        if (k < GLS_NCLASS - 1) {
-            int smem = h_gls_cap[k];
-            NPB_CUDA(cudaFuncSetAttribute(k_gls_nodes, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            int per_sm = (int)((227 * 1024) / (smem + 1024));
-            if (per_sm > 32) per_sm = 32;
-            int grid = c->sm_count * per_sm;
-            if (grid > count) grid = count;
-            k_gls_nodes<<<grid, 32, smem, s>>>(a, c->node_list, count, counter, nullptr, 0);
-        } else {
-            // oversized stars: global-memory workspace, sized for the largest possible system
-            int E = c->mx_epp, F = c->mx_fpp;
-            size_t stride = (gls_ws_bytes(E, E + 4 * F) + 255) & ~(size_t)255;
-            int grid = c->sm_count * 8;
-            if (grid > count) grid = count;
-            NPB_TRY(npb_ensure(&c->gls_ws, &c->gls_ws_cap, stride * (size_t)grid));
-            k_gls_nodes<<<grid, 32, 0, s>>>(a, c->node_list, count, counter, (double *)c->gls_ws, stride);
-        }
+        NpbTimer tk(c, cls_names[k]);
+        int smem = (int)mf_smem_bytes(h_mf[k]);
+        NPB_CUDA(cudaFuncSetAttribute(k_gls_mf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int per_sm = (int)((227 * 1024) / (smem + 1024));
+        if (per_sm > 32) per_sm = 32;
+        int grid = c->sm_count * per_sm;
+        if (grid > count) grid = count;
+        k_gls_mf<<<grid, 32, smem, s>>>(a, list, count, counter, k, overflow, n_overflow);
         NPB_LAUNCH(c);
         NPB_CUDA(cudaGetLastError());
-        // node_list is reused by the next class: the select below is stream-ordered after this kernel
+        tk.stop();
+        if (c->timings[cls_names[k]] > main_ms) main_ms = c->timings[cls_names[k]];
     }
-    NPB_CUDA(cudaStreamSynchronize(s));
-    NPB_CUDA(cudaFree(cls));
+    // dense fallback: stars classified as too large, then whatever overflowed at run time
+    {
+        NpbTimer tk(c, cls_names[MF_NCLASS - 1]);
+        NPB_TRY(npb_select_class(c, cls, lo, hi, MF_NCLASS - 1, list, &n_dense_direct));
+        NPB_TRY(npb_gls_dense(c, a, list, n_dense_direct));
+        int h_over = 0;
+        NPB_CUDA(cudaMemcpyAsync(&h_over, n_overflow, sizeof(int), cudaMemcpyDeviceToHost, s));
+        NPB_CUDA(cudaStreamSynchronize(s));
+        NPB_TRY(npb_gls_dense(c, a, overflow, h_over));
+        tk.stop();
+        c->timings["gls_dense_nodes"] = (float)(n_dense_direct + h_over);
+        if (c->timings[cls_names[MF_NCLASS - 1]] > main_ms && (n_dense_direct + h_over) > 0) main_ms = c->timings[cls_names[MF_NCLASS - 1]];
+    }
+    c->timings["k2_main"] = main_ms;
     return NPB_OK;
 }

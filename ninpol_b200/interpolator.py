@@ -72,7 +72,12 @@ class _Method:
 
 
 class Interpolator:
-    def __init__(self, name="interpolator", logging=False, build_edges=False, device=None, comm=None):
+    def __init__(self, name="interpolator", logging=False, build_edges=False, device=None, comm=None,
+                 pinned_outputs=False):
+        # pinned_outputs=True: the CSR / neumann arrays returned by interpolate() live in page-locked
+        # buffers that are REUSED by the next interpolate() call (faster device->host copies)
+        self.pinned_outputs = pinned_outputs
+        self._pinned = {}
         self.point_ordering = et.POINT_ORDERING
         self.is_grid_initialized = False
         self.build_edges = build_edges
@@ -83,9 +88,11 @@ class Interpolator:
         self.supported_methods = {"gls": self.gls.prepare, "idw": self.idw.prepare, "ls": self.ls.prepare}
         self.variable_to_index = {"points": {}, "cells": {}, "faces": {}}
         self.types_per_dimension = {k: list(v) for k, v in et.TYPES_PER_DIMENSION.items()}
-        self.cells_data = np.zeros((1, 1), dtype=DTYPE_F)
+        # per-variable rows; `cells_data` / `points_data` (the reference's [n_var, n*max_dim] arrays) are
+        # materialised from them on first access — at 50M cells the dense form alone is >10 GB
+        self._rows = {"cells": [], "points": []}
+        self._dense = {"cells": np.zeros((1, 1), dtype=DTYPE_F), "points": np.zeros((1, 1), dtype=DTYPE_F)}
         self.cells_data_dimensions = np.zeros(1, dtype=DTYPE_I)
-        self.points_data = np.zeros((1, 1), dtype=DTYPE_F)
         self.points_data_dimensions = np.zeros(1, dtype=DTYPE_I)
         self.faces_data = np.zeros((1, 1), dtype=DTYPE_F)
         self.faces_data_dimensions = np.zeros(1, dtype=DTYPE_I)
@@ -105,6 +112,23 @@ class Interpolator:
         self._staged = None
         self._partition_key = None
         self.last_timings = {}
+
+    def _dense_view(self, kind):
+        if self._dense[kind] is None:
+            rows = self._rows[kind]
+            width = max(len(r) for r in rows) if rows else 1
+            out = np.zeros((max(len(rows), 1), width), dtype=DTYPE_F)
+            for i, r in enumerate(rows):
+                out[i, :len(r)] = r
+            self._dense[kind] = out
+        return self._dense[kind]
+
+    def _set_dense(self, kind, value):
+        self._dense[kind] = value
+        self._rows[kind] = list(value)
+
+    cells_data = property(lambda self: self._dense_view("cells"), lambda self, v: self._set_dense("cells", v))
+    points_data = property(lambda self: self._dense_view("points"), lambda self, v: self._set_dense("points", v))
 
     # ------------------------------------------------------------------------------------------
     # cache helpers (interpolator.pyx:93-111) — inputs-only pickle cache, file meshes only
@@ -130,8 +154,9 @@ class Interpolator:
                 cache = pickle.load(f)
             args = cache["grid"]
             ic = cache["interpolator"]
-            self.cells_data, self.cells_data_dimensions = ic["cells_data"], ic["cells_data_dimensions"]
-            self.points_data, self.points_data_dimensions = ic["points_data"], ic["points_data_dimensions"]
+            self._set_dense("cells", ic["cells_data"])
+            self._set_dense("points", ic["points_data"])
+            self.cells_data_dimensions, self.points_data_dimensions = ic["cells_data_dimensions"], ic["points_data_dimensions"]
             self.faces_data, self.faces_data_dimensions = ic["faces_data"], ic["faces_data_dimensions"]
             self.variable_to_index, self.points_coords = ic["variable_to_index"], ic["points_coords"]
         else:
@@ -168,12 +193,12 @@ class Interpolator:
             if self.mesh_obj.cell_data:
                 self.load_cell_data()
             else:
-                self.cells_data = np.zeros((1, 1), dtype=DTYPE_F)
+                self._set_dense("cells", np.zeros((1, 1), dtype=DTYPE_F))
                 self.cells_data_dimensions = np.zeros(1, dtype=DTYPE_I)
             if self.mesh_obj.point_data:
                 self.load_point_data()
             else:
-                self.points_data = np.zeros((1, 1), dtype=DTYPE_F)
+                self._set_dense("points", np.zeros((1, 1), dtype=DTYPE_F))
                 self.points_data_dimensions = np.zeros(1, dtype=DTYPE_I)
             self.logger.log(f"Data loaded in {time.time() - t0:.2f} seconds")
         self.is_grid_initialized = True
@@ -226,27 +251,28 @@ class Interpolator:
     # load_data / load_cell_data / load_point_data (interpolator.pyx:372-454), vectorised
     # ------------------------------------------------------------------------------------------
     def load_data(self, data_dict, data_type):
+        """Row i of cells_data / points_data = variable i flattened (vectors item-major), zero padded to
+        n_items * max_dim — same content as the reference's per-item Python loops (:403-419)."""
         n_items = self.grid.n_elems if data_type == "cells" else self.grid.n_points
         dims = np.zeros(len(data_dict), dtype=DTYPE_I)
-        max_shape = 1
+        rows = [None] * len(data_dict)
         for index, variable in enumerate(data_dict):
             a = np.asarray(data_dict[variable])
             cur = a.shape[1] if a.ndim > 1 else 1
-            max_shape = max(max_shape, cur)
             self.variable_to_index[data_type][variable] = index
             dims[index] = cur
-        out = np.zeros((len(data_dict), n_items * max_shape), dtype=DTYPE_F)
-        for variable in data_dict:
-            index = self.variable_to_index[data_type][variable]
-            a = np.asarray(data_dict[variable])
-            if dims[index] == 1:
-                out[index, :n_items] = a[:n_items] if a.ndim == 1 else a[:n_items, 0]
+            if cur == 1:
+                r = a[:n_items] if a.ndim == 1 else a[:n_items, 0]
             else:
-                out[index, :n_items * dims[index]] = a[:n_items].reshape(-1)
+                r = a[:n_items].reshape(-1)
+            rows[index] = np.ascontiguousarray(r, dtype=DTYPE_F)
+        kind = "cells" if data_type == "cells" else "points"
+        self._rows[kind] = rows
+        self._dense[kind] = None
         if data_type == "cells":
-            self.cells_data_dimensions, self.cells_data = dims, out
+            self.cells_data_dimensions = dims
         else:
-            self.points_data_dimensions, self.points_data = dims, out
+            self.points_data_dimensions = dims
 
     def load_cell_data(self):
         dim = self.grid.dim
@@ -285,10 +311,10 @@ class Interpolator:
     def compute_diffusion_magnitude(permeability):
         """interpolator.pyx:501-509 as the RELEASE build evaluates it: `1 / 3` is C integer division
         (cdivision=True, setup.py:100-108), so det**0 == 1 and diff_mag = (1 - 3/tr K)^2."""
-        Ks = np.reshape(np.asarray(permeability, dtype=DTYPE_F), (len(permeability), 3, 3))
-        detKs = np.linalg.det(Ks)
-        trKs = np.trace(Ks, axis1=1, axis2=2)
-        return (1 - (3 * (detKs ** 0) / trKs)) ** 2
+        Ks = np.reshape(np.asarray(permeability, dtype=DTYPE_F), (len(permeability), 9))
+        trKs = (Ks[:, 0] + Ks[:, 4]) + Ks[:, 8]          # np.trace order
+        # 3 * det**0 == 3.0 exactly for every det (numpy: x**0 == 1, NaN and inf included)
+        return (1 - (3.0 / trKs)) ** 2
 
     def get_dict(self):
         return {"point_ordering": self.point_ordering, "variable_to_index": self.variable_to_index,
@@ -341,6 +367,11 @@ class Interpolator:
         self._flags_host = flags
         self._staged = key
 
+    def invalidate_inputs(self):
+        """Forget which per-variable inputs are resident on the device: the next interpolate() uploads
+        the flags (and, for GLS, permeability + diff_mag) again from host memory."""
+        self._staged = None
+
     def _set_partition(self, method):
         if self.comm.world == 1:
             return
@@ -355,15 +386,24 @@ class Interpolator:
         self._partition_key = key
         self.partition_bounds = bounds
 
+    def _out(self, name, n, dtype):
+        if not self.pinned_outputs:
+            return np.empty(n, dtype=dtype)
+        buf = self._pinned.get(name)
+        if buf is None or buf.size < n or buf.dtype != np.dtype(dtype):
+            buf = _capi.pinned_empty(n + n // 16 + 16, dtype)
+            self._pinned[name] = buf
+        return buf[:n]
+
     def _run(self, method):
         g = self.grid
         self._set_partition(method)
         nnz = self._ctx.interpolate_count(method)
         n_points = g.n_points
-        indptr = np.empty(n_points + 1, dtype=np.int32)
-        indices = np.empty(nnz, dtype=np.int32)
-        data = np.empty(nnz, dtype=np.float64)
-        neumann = np.empty(n_points, dtype=np.float64)
+        indptr = self._out("indptr", n_points + 1, np.int32)
+        indices = self._out("indices", nnz, np.int32)
+        data = self._out("data", nnz, np.float64)
+        neumann = self._out("neumann", n_points, np.float64)
         self._ctx.interpolate_fetch(indptr, indices, data, neumann)
         t = self._ctx.timing_or
         self.last_timings.update({"k2_ms": t("k2"), "k3_count_ms": t("k3_count"), "k3_fill_ms": t("k3_fill"),
@@ -383,7 +423,7 @@ class Interpolator:
             raise ValueError(f"Variable '{variable}' has more than one dimension. Vector data not supported yet.")
         self._check_targets(target_points)
         self.logger.log(f"Interpolating variable '{variable}' using method '{method}'")
-        self._stage_inputs(method, variable, self.variable_to_index, self.cells_data, self.points_data)
+        self._stage_inputs(method, variable, self.variable_to_index, self._rows["cells"], self._rows["points"])
         indptr, indices, data, neumann = self._run(method)
         g = self.grid
         # the device emitted canonical CSR (sorted, zero-free, int32 index arrays): no conversion, no copy

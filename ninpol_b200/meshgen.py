@@ -147,26 +147,43 @@ def mixed_box(n, a, b, perturb=0.25, seed=0):
 # ------------------------------------------------------------------------------------------------
 # fields
 # ------------------------------------------------------------------------------------------------
-def random_spd_permeability(n, seed=2, lam_decades=2.0, chunk=1 << 22):
+def _spd_chunk(args):
+    ss, count, lam_decades = args
+    rng = np.random.default_rng(ss)
+    q = rng.standard_normal((4, count))
+    q /= np.sqrt((q * q).sum(axis=0))
+    w, x, y, z = q
+    R = ((1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)),
+         (2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)),
+         (2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)))
+    lam = 10.0 ** rng.uniform(0.0, lam_decades, size=(3, count))
+    out = np.empty((count, 9), dtype=np.float64)
+    for a in range(3):
+        for b in range(a, 3):
+            v = lam[0] * R[a][0] * R[b][0] + lam[1] * R[a][1] * R[b][1] + lam[2] * R[a][2] * R[b][2]
+            out[:, 3 * a + b] = v
+            out[:, 3 * b + a] = v
+    return out
+
+
+def random_spd_permeability(n, seed=2, lam_decades=2.0, chunk=1 << 20, threads=None):
     """Heterogeneous anisotropic SPD tensors K = R diag(lambda) R^T flattened row-major to [n, 9]:
     R a uniformly random rotation (unit quaternion), lambda ~ 10^U(0, lam_decades), so tr K >= 3 and
-    the release-build diff_mag exponent eta = (1 - 3/tr K)^2 stays in [0, 1)."""
-    out = np.empty((n, 9), dtype=np.float64)
-    rng = np.random.default_rng(seed)
-    for s in range(0, n, chunk):
-        e = min(n, s + chunk)
-        q = rng.standard_normal((e - s, 4))
-        q /= np.linalg.norm(q, axis=1, keepdims=True)
-        w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
-        R = np.empty((e - s, 3, 3))
-        R[:, 0, 0] = 1 - 2 * (y * y + z * z); R[:, 0, 1] = 2 * (x * y - z * w); R[:, 0, 2] = 2 * (x * z + y * w)
-        R[:, 1, 0] = 2 * (x * y + z * w); R[:, 1, 1] = 1 - 2 * (x * x + z * z); R[:, 1, 2] = 2 * (y * z - x * w)
-        R[:, 2, 0] = 2 * (x * z - y * w); R[:, 2, 1] = 2 * (y * z + x * w); R[:, 2, 2] = 1 - 2 * (x * x + y * y)
-        lam = 10.0 ** rng.uniform(0.0, lam_decades, size=(e - s, 3))
-        K = np.einsum("nij,nj,nkj->nik", R, lam, R)
-        K = 0.5 * (K + K.transpose(0, 2, 1))
-        out[s:e] = K.reshape(-1, 9)
-    return out
+    the release-build diff_mag exponent eta = (1 - 3/tr K)^2 stays in [0, 1).
+    Deterministic for a given (n, seed, chunk): one PCG64 stream per chunk, spawned from `seed`."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    nchunks = max(1, (n + chunk - 1) // chunk)
+    seeds = np.random.SeedSequence(seed).spawn(nchunks)
+    jobs = [(seeds[i], min(chunk, n - i * chunk), lam_decades) for i in range(nchunks)]
+    if threads is None:
+        threads = min(16, os.cpu_count() or 1)
+    if nchunks == 1 or threads == 1:
+        parts = [_spd_chunk(j) for j in jobs]
+    else:
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            parts = list(ex.map(_spd_chunk, jobs))
+    return parts[0] if len(parts) == 1 else np.concatenate(parts, axis=0)
 
 
 def attach_fields(mesh, variable="u", seed=2, neumann_rate=0.5, hull_nodes=None, permeability=True):

@@ -1,0 +1,16 @@
+"""One load_mesh + interpolate pass on a synthetic mesh (profiling harness for ncu / compute-sanitizer).
+usage: python tools/run_once.py KIND N METHOD [REPEAT]"""
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ninpol_b200
+from ninpol_b200 import meshgen
+
+kind, n, method = sys.argv[1], int(sys.argv[2]), sys.argv[3]
+rep = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+mesh = meshgen.make_case(kind, n)
+I = ninpol_b200.Interpolator()
+I.load_mesh(mesh_obj=mesh)
+for _ in range(rep):
+    W, nv = I.interpolate("u", method)
+print(kind, n, method, "nnz", W.nnz, {k: round(v, 3) for k, v in I.last_timings.items()})
