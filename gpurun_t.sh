@@ -1,4 +1,5 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+python -m pytest tests -m gpu -x -q 2>&1 | tail -8
+for cfg in "tet 40" "hex 64" "mixed 24"; do python tools/run_once.py $cfg gls 2 2>&1 | tail -2; done
 python bench.py --workload tet69 --steps 2 --warmup 3 --also idw --no-cpu 2> gpurun_out/b69.err > gpurun_out/b69.json; tail -3 gpurun_out/b69.err
 python - <<'PY'
 import json

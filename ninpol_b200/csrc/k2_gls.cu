@@ -32,29 +32,29 @@
 
 typedef unsigned long long u64;
 
-#define MF_NCLASS 8          // 0 = skipped node, 1..6 = shared-memory classes, 7 = dense fallback
+#define MF_NCLASS 9          // 0 = skipped node, 1..7 = shared-memory classes, 8 = dense fallback
 #define MF_SCAP 64           // max row groups merged into one front
 
 struct MfClass {
-    int acap;   // arena capacity (doubles)
+    int acap;   // arena capacity (doubles); the global R slab of a CTA has the same capacity
     int ecap;   // max elements around the node
     int fcap;   // max faces around the node
 };
-__constant__ MfClass c_mf[MF_NCLASS] = {{0, 0, 0},        {1536, 12, 20},  {2560, 16, 28},  {4224, 24, 40},
-                                        {6144, 32, 56},   {9216, 48, 80},  {13312, 64, 112}, {0, 0, 0}};
-static const MfClass h_mf[MF_NCLASS] = {{0, 0, 0},        {1536, 12, 20},  {2560, 16, 28},  {4224, 24, 40},
-                                        {6144, 32, 56},   {9216, 48, 80},  {13312, 64, 112}, {0, 0, 0}};
+#define MF_CLASS_TABLE {{0, 0, 0}, {1152, 8, 14}, {1792, 12, 22}, {2560, 16, 30}, {3840, 24, 40}, {5632, 32, 56}, \
+                        {8704, 48, 80}, {12800, 64, 112}, {0, 0, 0}}
+__constant__ MfClass c_mf[MF_NCLASS] = MF_CLASS_TABLE;
+static const MfClass h_mf[MF_NCLASS] = MF_CLASS_TABLE;
 
-__host__ __device__ __forceinline__ int mf_ngcap(const MfClass &k) { return k.ecap + k.fcap + 2 * k.ecap; }
+__host__ __device__ __forceinline__ int mf_ngcap(const MfClass &k) { return ((2 * k.ecap + k.fcap + 7) / 8) * 8; }
 __host__ __device__ __forceinline__ int mf_mcap(const MfClass &k) { int m = k.ecap + 4 * k.fcap; return m < 96 ? m : 96; }
 __host__ __device__ __forceinline__ size_t mf_smem_bytes(const MfClass &k)
 {
     size_t d = (size_t)k.acap + 4 * (size_t)mf_mcap(k) + 6 * (size_t)k.ecap;  // arena, vbuf[.][4], gvec, dvec
-    size_t b = d * 8 + (size_t)mf_ngcap(k) * (8 + 4 + 2 + 1 + 1 + 1 + 1);   // group table
+    size_t b = d * 8 + (size_t)mf_ngcap(k) * (8 + 4 + 2 + 1) + (size_t)k.ecap * (8 + 4 + 4);   // group table, R table
     b += (size_t)k.ecap * 4 + MF_SCAP * 4 + 64;                             // es, S list, colblk
     return (b + 15) & ~(size_t)15;
 }
-__host__ __device__ __forceinline__ int mf_arena_need(int E, int m) { return 30 * m + 4 * E + 128; }
+__host__ __device__ __forceinline__ int mf_arena_need(int E, int m) { (void)E; return 22 * m + 64; }
 
 // per node: Dirichlet / Q8 nodes are finished here (zero row); the others get a size class
 __global__ void k_gls_classify(GlsArgs a, i64 lo, i64 hi, uint8_t *__restrict__ cls)
@@ -104,10 +104,10 @@ __device__ __forceinline__ int nth_set_bit(u64 m, int n)  // index of the n-th (
 
 struct MfWs {
     double *arena, *vbuf, *gvec, *dvec;
-    u64 *g_mask;
-    int *g_off;
+    u64 *g_mask, *r_mask;
+    int *g_off, *r_off, *r_meta;   // r_meta = piv | npiv << 8 | c << 16
     unsigned short *g_nr;
-    unsigned char *g_ld, *g_kind, *g_piv;
+    unsigned char *g_ld;
     int *es;
     int *s_list;            // packed (gid | rowbase << 16)
     unsigned char *colblk;  // block id of every 3-column slot of the current front
@@ -122,42 +122,53 @@ __device__ __forceinline__ MfWs mf_carve(unsigned char *base, const MfClass &k)
     w.gvec = w.vbuf + 4 * mf_mcap(k);
     w.dvec = w.gvec + 3 * k.ecap;
     w.g_mask = (u64 *)(w.dvec + 3 * k.ecap);
-    w.g_off = (int *)(w.g_mask + ng);
-    w.es = w.g_off + ng;
+    w.r_mask = w.g_mask + ng;
+    w.g_off = (int *)(w.r_mask + k.ecap);
+    w.r_off = w.g_off + ng;
+    w.r_meta = w.r_off + k.ecap;
+    w.es = w.r_meta + k.ecap;
     w.s_list = w.es + k.ecap;
     w.g_nr = (unsigned short *)(w.s_list + MF_SCAP);
     w.g_ld = (unsigned char *)(w.g_nr + ng);
-    w.g_kind = w.g_ld + ng;
-    w.g_piv = w.g_kind + ng;
-    w.colblk = w.g_piv + ng;                    // [64]
+    w.colblk = w.g_ld + ng;                     // [64]
     return w;
 }
 
-// Slides every live table entry down to close the holes left by consumed groups.  Table order equals
-// arena order (entries are only ever appended at the arena top), so a forward pass is a safe memmove.
-__device__ int mf_compact(MfWs &w, int ng, int lane)
+// Closes the holes left by consumed groups: live table entries (and their arena blocks) slide down in
+// table order, which equals arena order because entries are only ever appended at the arena top.
+__device__ void mf_compact(MfWs &w, int &ng, int &top, int lane)
 {
-    int top = 0;
-    for (int g = 0; g < ng; g++) {
-        int nr = w.g_nr[g];
-        if (nr == 0) continue;
-        int sz = nr * (int)w.g_ld[g];
-        int src = w.g_off[g];
-        if (src != top) {
-            for (int i0 = 0; i0 < sz; i0 += 32) {
-                int i = i0 + lane;
-                double v = 0.0;
-                if (i < sz) v = w.arena[src + i];
-                __syncwarp();
-                if (i < sz) w.arena[top + i] = v;
-                __syncwarp();
+    int newng = 0, newtop = 0;
+    for (int g0 = 0; g0 < ng; g0 += 32) {
+        int g = g0 + lane;
+        unsigned bal = __ballot_sync(0xffffffffu, g < ng && w.g_nr[g] > 0);
+        while (bal) {
+            int gi = g0 + __ffs(bal) - 1;
+            bal &= bal - 1;
+            u64 mk = w.g_mask[gi];
+            int src = w.g_off[gi], nr = w.g_nr[gi], ld = w.g_ld[gi];
+            int sz = nr * ld;
+            if (src != newtop) {
+                for (int i = lane; i < sz; i += 32) {
+                    double v = w.arena[src + i];
+                    __syncwarp(__activemask());
+                    w.arena[newtop + i] = v;
+                }
             }
-            if (lane == 0) w.g_off[g] = top;
+            __syncwarp();
+            if (lane == 0) {
+                w.g_mask[newng] = mk;
+                w.g_off[newng] = newtop;
+                w.g_nr[newng] = (unsigned short)nr;
+                w.g_ld[newng] = (unsigned char)ld;
+            }
+            newtop += sz;
+            newng++;
         }
-        top += sz;
     }
     __syncwarp();
-    return top;
+    ng = newng;
+    top = newtop;
 }
 
 #define MF_RPL 3   // front rows per lane in the panel factorisation: fronts of up to 96 rows
@@ -175,7 +186,7 @@ __device__ __forceinline__ void hh_scalars(double sigma, double x0, double &alph
 }
 
 // returns 0 on success, 1 when the star does not fit this class (caller reroutes it to the dense kernel)
-__device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfClass &kc)
+__device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfClass &kc, double *rslab)
 {
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
@@ -199,7 +210,6 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
         w.g_off[i] = 4 * i;
         w.g_nr[i] = 1;
         w.g_ld[i] = 4;
-        w.g_kind[i] = 0;
     }
     // ---- face groups (gls.pyx:291-356) and Neumann groups (:394-416) ----
     int n_if = 0;
@@ -262,7 +272,6 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
             w.g_off[g] = off_if + 21 * j;
             w.g_nr[g] = 3;
             w.g_ld[g] = 7;
-            w.g_kind[g] = 0;
         }
         if (boundary && neu) {
             int j = bf_seen + __popc(mb & below);
@@ -281,7 +290,6 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
             w.g_off[g] = off_bf + 4 * j;
             w.g_nr[g] = 1;
             w.g_ld[g] = 4;
-            w.g_kind[g] = 0;
         }
         if_seen += __popc(mi);
         bf_seen += __popc(mb);
@@ -301,6 +309,7 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
         }
     }
     u64 alive = (E >= 64) ? ~0ull : ((1ull << E) - 1ull);
+    int nR = 0, rtop = 0;   // R rows written so far (entries / doubles in the global slab)
 
     // ---- elimination ----
     while (alive) {
@@ -310,45 +319,46 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
         unsigned key = __reduce_min_sync(FULL, keyA < keyB ? keyA : keyB);
         const int piv = (int)(key & 0xffu);
         const u64 pbit = 1ull << piv;
-        // (b) row groups containing the pivot block
-        int nS = 0, rho = 0;
-        u64 U = 0;
-        for (int g0 = 0; g0 < ng; g0 += 32) {
-            int g = g0 + lane;
-            bool in = false;
-            int nr = 0;
-            u64 mk = 0;
-            if (g < ng) {
-                nr = w.g_nr[g];
-                mk = w.g_mask[g];
-                in = nr > 0 && w.g_kind[g] == 0 && (mk & pbit);
-            }
-            unsigned bal = __ballot_sync(FULL, in);
-            if (bal == 0) continue;
-            int v = in ? nr : 0;   // exclusive prefix of the row counts over the selected lanes
-            int incl = v;
+        // (b) row groups containing the pivot block; (c) room for the front at the arena top
+        int nS, rho, c, need;
+        u64 U, Up;
+        for (int attempt = 0;; attempt++) {
+            nS = 0; rho = 0; U = 0;
+            for (int g0 = 0; g0 < ng; g0 += 32) {
+                int g = g0 + lane;
+                bool in = false;
+                int nr = 0;
+                u64 mk = 0;
+                if (g < ng) {
+                    nr = w.g_nr[g];
+                    mk = w.g_mask[g];
+                    in = nr > 0 && (mk & pbit);
+                }
+                unsigned bal = __ballot_sync(FULL, in);
+                if (bal == 0) continue;
+                int v = in ? nr : 0;   // exclusive prefix of the row counts over the selected lanes
+                int incl = v;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int t = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += t;
+                for (int o = 1; o < 32; o <<= 1) {
+                    int t = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                int pos = nS + __popc(bal & ((1u << lane) - 1u));
+                if (in && pos < MF_SCAP) w.s_list[pos] = g | ((rho + incl - v) << 16);
+                nS += __popc(bal);
+                rho += __shfl_sync(FULL, incl, 31);
+                U |= warp_or64(in ? mk : 0ull);
             }
-            int pos = nS + __popc(bal & ((1u << lane) - 1u));
-            if (in && pos < MF_SCAP) w.s_list[pos] = g | ((rho + incl - v) << 16);
-            nS += __popc(bal);
-            rho += __shfl_sync(FULL, incl, 31);
-            U |= warp_or64(in ? mk : 0ull);
+            if (nS > MF_SCAP || rho > 32 * MF_RPL || rho > mf_mcap(kc)) return 1;
+            Up = U & ~pbit;
+            c = 3 * __popcll(U) + 1;
+            need = rho * c;
+            if (top + need <= kc.acap) break;
+            if (attempt > 0) return 1;
+            __syncwarp();
+            mf_compact(w, ng, top, lane);   // renumbers the table: select again
         }
-        if (nS > MF_SCAP || rho > 32 * MF_RPL) return 1;
-        const u64 Up = U & ~pbit;
-        const int nblk = __popcll(U);
-        const int c = 3 * nblk + 1;
-        const int need = rho * c;
-        // (c) room for the front at the arena top
-        if (top + need > kc.acap) {
-            top = mf_compact(w, ng, lane);
-            if (top + need > kc.acap) return 1;
-        }
-        if (ng + 2 > ngcap || rho > mf_mcap(kc)) return 1;
+        if (ng + 1 > ngcap || rtop + 3 * c > kc.acap) return 1;
         // block id of every column slot: slot 0 = pivot, then the other blocks ascending
         if ((Up >> lane) & 1ull) w.colblk[1 + __popcll(Up & ((1ull << lane) - 1ull))] = (unsigned char)lane;
         if ((Up >> (lane + 32)) & 1ull) w.colblk[1 + __popcll(Up & ((1ull << (lane + 32)) - 1ull))] = (unsigned char)(lane + 32);
@@ -494,25 +504,28 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
             }
         }
         __syncwarp();
-        // (g) table entries: the pivot rows (rows of R) and the remaining rows as one new group
+        // (g) the pivot rows go to the R slab (global, L2-resident); the remaining rows stay as a new group
         const int npiv = rho < 3 ? rho : 3;
         const int left = rho - npiv;
         const bool keep = left > 0 && Up != 0;
+        for (int j = lane; j < npiv * c; j += 32) rslab[rtop + j] = Fm[j];
         if (lane == 0) {
-            w.g_mask[ng] = U;
-            w.g_off[ng] = top;
-            w.g_nr[ng] = (unsigned short)npiv;
-            w.g_ld[ng] = (unsigned char)c;
-            w.g_kind[ng] = 1;
-            w.g_piv[ng] = (unsigned char)piv;
-            w.g_mask[ng + 1] = Up;
-            w.g_off[ng + 1] = top + npiv * c + 3;
-            w.g_nr[ng + 1] = (unsigned short)(keep ? left : 0);
-            w.g_ld[ng + 1] = (unsigned char)c;
-            w.g_kind[ng + 1] = 0;
+            w.r_mask[nR] = U;
+            w.r_off[nR] = rtop;
+            w.r_meta[nR] = piv | (npiv << 8) | (c << 16);
+            if (keep) {
+                w.g_mask[ng] = Up;
+                w.g_off[ng] = top + npiv * c + 3;
+                w.g_nr[ng] = (unsigned short)left;
+                w.g_ld[ng] = (unsigned char)c;
+            }
         }
-        top += keep ? need : npiv * c;
-        ng += 2;
+        nR++;
+        rtop += npiv * c;
+        if (keep) {
+            top += need;
+            ng++;
+        }
         // (h) adjacency update: the neighbours of the pivot become a clique
         if ((Up >> lane) & 1ull) adjA = (adjA | U) & ~pbit;
         if ((Up >> (lane + 32)) & 1ull) adjB = (adjB | U) & ~pbit;
@@ -520,14 +533,16 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
         __syncwarp();
     }
 
-    // ---- back substitution through the R entries, newest first ----
+    // ---- back substitution through the R rows, newest first (slab copied back into the free arena) ----
+    __syncwarp();
+    for (int i = lane; i < rtop; i += 32) w.arena[i] = rslab[i];
     for (int i = lane; i < 3 * E; i += 32) w.gvec[i] = 0.0;
     __syncwarp();
-    for (int g = ng - 2; g >= 0; g--) {
-        if (w.g_kind[g] != 1) continue;
-        const int npiv = w.g_nr[g], c = w.g_ld[g], piv = w.g_piv[g];
-        const u64 Up = w.g_mask[g] & ~(1ull << piv);
-        const double *R = w.arena + w.g_off[g];
+    for (int g = nR - 1; g >= 0; g--) {
+        const int meta = w.r_meta[g];
+        const int piv = meta & 0xff, npiv = (meta >> 8) & 0xff, c = meta >> 16;
+        const u64 Up = w.r_mask[g] & ~(1ull << piv);
+        const double *R = w.arena + w.r_off[g];
         double p0 = 0.0, p1 = 0.0, p2 = 0.0;
         for (int j0 = 3; j0 < c - 1; j0 += 32) {
             int j = j0 + lane;
@@ -595,17 +610,18 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
 // appended to the overflow list for the dense kernel
 __global__ void __launch_bounds__(32)
 k_gls_mf(GlsArgs a, const int32_t *__restrict__ list, int count, int *__restrict__ counter, int klass,
-         int32_t *__restrict__ overflow, int *__restrict__ n_overflow)
+         int32_t *__restrict__ overflow, int *__restrict__ n_overflow, double *__restrict__ rslabs)
 {
     extern __shared__ __align__(16) unsigned char smem_mf[];
     const MfClass kc = c_mf[klass];
+    double *rslab = rslabs + (size_t)blockIdx.x * kc.acap;
     while (true) {
         int i = 0;
         if (threadIdx.x == 0) i = atomicAdd(counter, 1);
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= count) break;
         int p = list[i];
-        int rc = mf_node(a, p, smem_mf, kc);
+        int rc = mf_node(a, p, smem_mf, kc, rslab);
         __syncwarp();
         if (rc != 0 && threadIdx.x == 0) overflow[atomicAdd(n_overflow, 1)] = p;
     }
@@ -632,7 +648,7 @@ int npb_k2_gls(npb_ctx *c, i64 lo, i64 hi)
     k_gls_classify<<<npb_blocks(nloc, 256), 256, 0, s>>>(a, lo, hi, cls);
     NPB_LAUNCH(c);
     float main_ms = 0.f;
-    static const char *cls_names[MF_NCLASS] = {"", "k2_gls_c1", "k2_gls_c2", "k2_gls_c3", "k2_gls_c4", "k2_gls_c5", "k2_gls_c6", "k2_gls_dense"};
+    static const char *cls_names[MF_NCLASS] = {"", "k2_gls_c1", "k2_gls_c2", "k2_gls_c3", "k2_gls_c4", "k2_gls_c5", "k2_gls_c6", "k2_gls_c7", "k2_gls_dense"};
     for (int k = 1; k < MF_NCLASS; k++) c->timings.erase(cls_names[k]);
     int n_dense_direct = 0;
     for (int k = 1; k < MF_NCLASS - 1; k++) {
@@ -648,7 +664,8 @@ int npb_k2_gls(npb_ctx *c, i64 lo, i64 hi)
         if (per_sm > 32) per_sm = 32;
         int grid = c->sm_count * per_sm;
         if (grid > count) grid = count;
-        k_gls_mf<<<grid, 32, smem, s>>>(a, list, count, counter, k, overflow, n_overflow);
+        NPB_TRY(npb_ensure(&c->gls_ws, &c->gls_ws_cap, sizeof(double) * (size_t)grid * h_mf[k].acap));
+        k_gls_mf<<<grid, 32, smem, s>>>(a, list, count, counter, k, overflow, n_overflow, (double *)c->gls_ws);
         NPB_LAUNCH(c);
         NPB_CUDA(cudaGetLastError());
         tk.stop();

@@ -14,5 +14,5 @@ I.load_mesh(mesh_obj=mesh)
 for _ in range(rep):
     W, nv = I.interpolate("u", method)
 print(kind, n, method, "nnz", W.nnz, {k: round(v, 3) for k, v in I.last_timings.items()})
-names = ["k2", "k2_main", "k2_gls_c1", "k2_gls_c2", "k2_gls_c3", "k2_gls_c4", "k2_gls_c5", "k2_gls_c6", "k2_gls_dense", "gls_dense_nodes"]
+names = ["k2", "k2_main", "k2_gls_c1", "k2_gls_c2", "k2_gls_c3", "k2_gls_c4", "k2_gls_c5", "k2_gls_c6", "k2_gls_c7", "k2_gls_dense", "gls_dense_nodes"]
 print({n: round(I._ctx.timing_or(n, -1), 3) for n in names})
