@@ -81,6 +81,7 @@ static void free_mesh(npb_ctx *c)
     c->coords = c->centroids = c->fcent = c->fnormal = c->farea = c->perm = c->diff_mag = c->neumann = nullptr;
     c->rowcnt = c->indptr = nullptr;
     c->have_perm = c->have_dm = c->have_flags = false;
+    c->fused_failed[0] = c->fused_failed[1] = false;
     c->mesh_loaded = false;
     c->counted = false;
 }
@@ -371,6 +372,7 @@ extern "C" int npb_set_point_flags(npb_ctx *c, const int64_t *flag, int64_t n_po
     NPB_CUDA(cudaFree(tmp));
     c->have_flags = true;
     c->counted = false;
+    c->fused_failed[0] = c->fused_failed[1] = false;
     return NPB_OK;
 }
 
@@ -398,15 +400,39 @@ extern "C" int npb_interpolate_count(npb_ctx *c, int method, int64_t *nnz)
     }
     NPB_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
+    c->filled = false;
+    if (method != NPB_METHOD_GLS && !c->fused_failed[method]) {
+        // fused K2+K3 (k2_idw_ls_tile.cu): final CSR in one pass unless a weight is an exact zero
+        NpbTimer tm(c, "k2");
+        int used = 0;
+        NPB_TRY(npb_k2_idw_ls_fused(c, method, &used));
+        tm.stop();
+        if (!used && c->world == 1) c->fused_failed[method] = true;   // same inputs -> same zeros next time
+        if (used) {
+            c->timings["k3_count"] = 0.f;
+            c->timings["k3_fill"] = 0.f;
+            c->method = method;
+            c->counted = true;
+            c->filled = true;
+            *nnz = c->nnz;
+            return NPB_OK;
+        }
+    }
     NPB_TRY(npb_ensure((void **)&c->wbuf, &c->wbuf_cap, sizeof(double) * (size_t)(c->wlen > 0 ? c->wlen : 1)));
     {
         NpbTimer tm(c, "k2");
         if (method == NPB_METHOD_GLS)
             NPB_TRY(npb_k2_gls(c, c->lo, c->hi));
-        else
-            NPB_TRY(npb_k2_idw_ls(c, method, c->lo, c->hi));
+        else {
+            int used = 0;
+            NPB_TRY(npb_k2_idw_ls_tiles(c, method, c->lo, c->hi, &used));
+            if (!used) {
+                NPB_TRY(npb_k2_idw_ls(c, method, c->lo, c->hi));
+                c->timings.erase("k2_main");
+            }
+        }
         tm.stop();
-        if (method != NPB_METHOD_GLS) c->timings["k2_main"] = c->timings["k2"];
+        if (method != NPB_METHOD_GLS && !c->timings.count("k2_main")) c->timings["k2_main"] = c->timings["k2"];
     }
     {
         NpbTimer tm(c, "k3_count");
@@ -428,6 +454,22 @@ extern "C" int npb_interpolate_count(npb_ctx *c, int method, int64_t *nnz)
     return NPB_OK;
 }
 
+int npb_ensure_out(npb_ctx *c, size_t n)
+{
+    size_t n1 = n > 0 ? n : 1;
+    if (c->out_cap >= n1) return NPB_OK;
+    if (c->indices) NPB_CUDA(cudaFree(c->indices));
+    if (c->data) NPB_CUDA(cudaFree(c->data));
+    c->indices = nullptr;
+    c->data = nullptr;
+    c->out_cap = 0;
+    size_t want = n1 + n1 / 16 + 64;
+    NPB_CUDA(cudaMalloc(&c->indices, sizeof(int32_t) * want));
+    NPB_CUDA(cudaMalloc(&c->data, sizeof(double) * want));
+    c->out_cap = want;
+    return NPB_OK;
+}
+
 extern "C" int npb_interpolate_fetch(npb_ctx *c, int32_t *indptr, int32_t *indices, double *data, double *neumann)
 {
     if (!c) return NPB_ERR_ARG;
@@ -437,22 +479,12 @@ extern "C" int npb_interpolate_fetch(npb_ctx *c, int32_t *indptr, int32_t *indic
     }
     NPB_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
-    size_t n1 = (size_t)(c->nnz > 0 ? c->nnz : 1);
-    if (c->out_cap < n1) {
-        if (c->indices) NPB_CUDA(cudaFree(c->indices));
-        if (c->data) NPB_CUDA(cudaFree(c->data));
-        c->indices = nullptr;
-        c->data = nullptr;
-        c->out_cap = 0;
-        size_t want = n1 + n1 / 16 + 64;
-        NPB_CUDA(cudaMalloc(&c->indices, sizeof(int32_t) * want));
-        NPB_CUDA(cudaMalloc(&c->data, sizeof(double) * want));
-        c->out_cap = want;
-    }
-    {
+    if (!c->filled) {
+        NPB_TRY(npb_ensure_out(c, (size_t)c->nnz));
         NpbTimer tm(c, "k3_fill");
         NPB_TRY(npb_k3_fill(c, c->lo, c->hi));
         tm.stop();
+        c->filled = true;
     }
     if (c->world > 1) {
         NpbTimer tm(c, "k4_gather");

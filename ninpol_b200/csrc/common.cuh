@@ -98,6 +98,8 @@ struct npb_ctx {
     // ---- interpolate state ----
     int method = -1;
     bool counted = false;
+    bool fused_failed[2] = {false, false};   // per method: the single-pass emit met an exact zero for the current inputs
+    bool filled = false;         // indices / data already hold the CSR (fused path, or k3_fill done)
     i64 nnz = 0;
     double *wbuf = nullptr;      // final data values, esup-indexed, local node range
     size_t wbuf_cap = 0;
@@ -137,6 +139,9 @@ int npb_k1_build(npb_ctx *c, const i64 *h_conn, const i64 *h_types, const double
 int npb_k1_geometry(npb_ctx *c);
 int npb_k1_extras(npb_ctx *c);  // psup, edges
 int npb_k2_idw_ls(npb_ctx *c, int method, i64 lo, i64 hi);
+int npb_k2_idw_ls_fused(npb_ctx *c, int method, int *used);
+int npb_k2_idw_ls_tiles(npb_ctx *c, int method, i64 lo, i64 hi, int *used);
+int npb_ensure_out(npb_ctx *c, size_t n);
 int npb_k2_gls(npb_ctx *c, i64 lo, i64 hi);
 int npb_k3_fill(npb_ctx *c, i64 lo, i64 hi);
 int npb_k4_gather_counts(npb_ctx *c);

@@ -28,6 +28,7 @@
 // star size so small stars get many resident warps; stars that do not fit (E > 64, arena overflow) go
 // to the dense global-memory kernel of k2_gls_dense.cu.  FP64-FMA / shared-memory bound, not HBM bound
 // (SURVEY.md Q13).
+#include <stdlib.h>
 #include "gls_common.cuh"
 
 typedef unsigned long long u64;
@@ -57,7 +58,7 @@ __host__ __device__ __forceinline__ size_t mf_smem_bytes(const MfClass &k)
 __host__ __device__ __forceinline__ int mf_arena_need(int E, int m) { (void)E; return 22 * m + 64; }
 
 // per node: Dirichlet / Q8 nodes are finished here (zero row); the others get a size class
-__global__ void k_gls_classify(GlsArgs a, i64 lo, i64 hi, uint8_t *__restrict__ cls)
+__global__ void k_gls_classify(GlsArgs a, i64 lo, i64 hi, uint8_t *__restrict__ cls, int force_dense)
 {
     i64 p = lo + (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= hi) return;
@@ -82,7 +83,7 @@ __global__ void k_gls_classify(GlsArgs a, i64 lo, i64 hi, uint8_t *__restrict__ 
     int m = E + 3 * (F - nb) + (neu ? nb : 0);
     int need = mf_arena_need(E, m);
     int k = MF_NCLASS - 1;
-    for (int q = 1; q < MF_NCLASS - 1; q++)
+    for (int q = 1; q < MF_NCLASS - 1 && !force_dense; q++)
         if (E <= c_mf[q].ecap && F <= c_mf[q].fcap && need <= c_mf[q].acap) {
             k = q;
             break;
@@ -645,7 +646,8 @@ int npb_k2_gls(npb_ctx *c, i64 lo, i64 hi)
     uint8_t *cls = (uint8_t *)(c->node_list + 2 * c->n_points);
     int *n_overflow = c->counters + 40;
     NPB_CUDA(cudaMemsetAsync(n_overflow, 0, sizeof(int), s));
-    k_gls_classify<<<npb_blocks(nloc, 256), 256, 0, s>>>(a, lo, hi, cls);
+    const char *force = getenv("NPB_FORCE_GLS_DENSE");   // tests: exercise the dense fallback kernel
+    k_gls_classify<<<npb_blocks(nloc, 256), 256, 0, s>>>(a, lo, hi, cls, (force && force[0] == '1') ? 1 : 0);
     NPB_LAUNCH(c);
     float main_ms = 0.f;
     static const char *cls_names[MF_NCLASS] = {"", "k2_gls_c1", "k2_gls_c2", "k2_gls_c3", "k2_gls_c4", "k2_gls_c5", "k2_gls_c6", "k2_gls_c7", "k2_gls_dense"};

@@ -139,3 +139,21 @@ def test_errors_match_reference_conventions():
     assert list(I.supported_methods) == ["gls", "idw", "ls"]
     W, nv = I.interpolate("u", "idw", target_points=np.arange(I.grid.n_points, dtype=np.int64))
     assert W.shape == (I.grid.n_points, I.grid.n_elems)
+
+
+@pytest.mark.parametrize("kind,n,kw", [("tet", 9, {}), ("hex", 10, {}), ("mixed", 8, {"a": 2, "b": 4})])
+def test_fallback_kernels_agree(kind, n, kw, monkeypatch):
+    """The general-purpose fallbacks (thread-per-node IDW/LS + two-pass emit; dense Householder GLS) must
+    give the same answers as the fast paths: bit-exact for IDW/LS, <= 1e-12 for GLS."""
+    monkeypatch.setenv("NPB_FORCE_SIMPLE_IDW_LS", "1")
+    monkeypatch.setenv("NPB_FORCE_GLS_DENSE", "1")
+    I, O = _pair(kind, n, kw)
+    for method in ("idw", "ls", "gls"):
+        W, nv = I.interpolate("u", method)
+        Wo, nvo = O.interpolate("u", method)
+        assert np.array_equal(W.indptr, Wo.indptr) and np.array_equal(W.indices, Wo.indices)
+        if method == "gls":
+            assert gls_errors(W, Wo) <= GLS_TOL
+        else:
+            assert np.array_equal(W.data, Wo.data, equal_nan=True)
+            assert np.array_equal(nv, nvo)
