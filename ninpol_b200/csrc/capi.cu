@@ -48,7 +48,7 @@ int npb_ensure(void **p, size_t *cap, size_t bytes)
     return NPB_OK;
 }
 
-NpbTimer::NpbTimer(npb_ctx *c_, const char *n) : c(c_), name(n), a(nullptr), b(nullptr)
+NpbTimer::NpbTimer(npb_ctx *c_, const char *n, bool accumulate_) : c(c_), name(n), a(nullptr), b(nullptr), accumulate(accumulate_)
 {
     cudaEventCreate(&a);
     cudaEventCreate(&b);
@@ -61,7 +61,10 @@ void NpbTimer::stop()
     cudaEventSynchronize(b);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, a, b);
-    c->timings[name] = ms;
+    if (accumulate)
+        c->timings[name] += ms;
+    else
+        c->timings[name] = ms;
     cudaEventDestroy(a);
     cudaEventDestroy(b);
     a = b = nullptr;

@@ -125,7 +125,8 @@ struct NpbTimer {
     npb_ctx *c;
     const char *name;
     cudaEvent_t a, b;
-    NpbTimer(npb_ctx *c_, const char *n);
+    bool accumulate;
+    NpbTimer(npb_ctx *c_, const char *n, bool accumulate_ = false);   // accumulate: add to timings[name]
     void stop();
 };
 

@@ -76,9 +76,18 @@ __global__ void k_sort_rows(const int32_t *__restrict__ ptr, i64 n_rows, int32_t
 // face order) wins.  On conforming meshes the match is unique, so the reference's reverse write
 // esuel[jelem,l] = ielem (:517) is what the thread of (jelem,l) finds by itself.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_esuel(ElemTables tab, const int32_t *__restrict__ inpoel, const uint8_t *__restrict__ etype,
-                        const int32_t *__restrict__ esup_ptr, const int32_t *__restrict__ esup, i64 n_elems, int spe,
-                        int sfe, int32_t *__restrict__ esuel)
+// The candidate test is evaluated with bitmasks: `hit` has bit k set when local node k of the candidate
+// belongs to this face; face l of the candidate matches iff popc(hit & nodes_of_face[l]) equals the
+// number of nodes of this face — literally the count `is_equal` of grid.pyx:503-512.
+struct FaceMasks {
+    unsigned char m[NPB_N_TYPES][NPB_MX_FE];
+};
+
+template <int SPE>
+__global__ void __launch_bounds__(256)
+k_esuel(ElemTables tab, FaceMasks fm, const int32_t *__restrict__ inpoel, const uint8_t *__restrict__ etype,
+        const int32_t *__restrict__ esup_ptr, const int32_t *__restrict__ esup, i64 n_elems, int sfe,
+        int32_t *__restrict__ esuel)
 {
     i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_elems * sfe) return;
@@ -89,10 +98,10 @@ __global__ void k_esuel(ElemTables tab, const int32_t *__restrict__ inpoel, cons
         esuel[idx] = -1;
         return;
     }
-    int nj = tab.lnofa[t][j];
+    const int nj = tab.lnofa[t][j];
     int mine[NPB_MX_PF];
 #pragma unroll
-    for (int o = 0; o < NPB_MX_PF; o++) mine[o] = (o < nj) ? inpoel[e * spe + tab.lpofa[t][j][o]] : -2;
+    for (int o = 0; o < NPB_MX_PF; o++) mine[o] = (o < nj) ? inpoel[e * SPE + tab.lpofa[t][j][o]] : -2;
     int point = mine[0];
     int nmin = esup_ptr[point + 1] - esup_ptr[point];
 #pragma unroll
@@ -106,27 +115,32 @@ __global__ void k_esuel(ElemTables tab, const int32_t *__restrict__ inpoel, cons
         }
     }
     int res = -1;
-    int qb = esup_ptr[point], qe = esup_ptr[point + 1];
-    for (int q = qb; q < qe && res < 0; q++) {
+    const int qb = esup_ptr[point], qe = esup_ptr[point + 1];
+    for (int q = qb; q < qe; q++) {
         int je = esup[q];
         if (je == (int)e) continue;
-        int jt = etype[je];
-        const int32_t *rowj = inpoel + (i64)je * spe;
-        int nf = tab.nfael[jt];
-        for (int l = 0; l < nf; l++) {
-            int eq = 0;
-            int nl = tab.lnofa[jt][l];
-            for (int m = 0; m < nl; m++) {
-                int qn = rowj[tab.lpofa[jt][l][m]];
-                bool hit = false;
+        int row[SPE];
+        const int4 *rp = reinterpret_cast<const int4 *>(inpoel + (i64)je * SPE);
 #pragma unroll
-                for (int o = 0; o < NPB_MX_PF; o++) hit = hit || (qn == mine[o]);
-                eq += hit ? 1 : 0;
-            }
-            if (eq == nj) {
-                res = je;
-                break;
-            }
+        for (int v = 0; v < SPE / 4; v++) {
+            int4 x = rp[v];
+            row[4 * v] = x.x; row[4 * v + 1] = x.y; row[4 * v + 2] = x.z; row[4 * v + 3] = x.w;
+        }
+        unsigned hit = 0;
+#pragma unroll
+        for (int k = 0; k < SPE; k++) {
+            int qn = row[k];
+            bool h = (qn == mine[0]) | (qn == mine[1]) | (qn == mine[2]) | (qn == mine[3]);
+            hit |= h ? (1u << k) : 0u;
+        }
+        if (__popc(hit) < nj) continue;       // cannot match any face
+        int jt = etype[je];
+        int nf = tab.nfael[jt];
+        bool match = false;
+        for (int l = 0; l < nf; l++) match = match || (__popc(hit & fm.m[jt][l]) == nj);
+        if (match) {
+            res = je;
+            break;
         }
     }
     esuel[idx] = res;
@@ -250,25 +264,38 @@ int npb_k1_build(npb_ctx *c, const i64 *h_conn, const i64 *h_types, const double
         NPB_CUDA(cudaFree(d_conn));
         NPB_CUDA(cudaFree(d_types));
     }
-    NpbTimer tk1(c, "k1");
-    int *d_mx = c->counters;  // [0] = mx_epp, [1] = mx_fpp
+    // Device time of K1 = sum of the kernel segments below; cudaMalloc / host round trips for the sizes
+    // (n_faces, row totals) sit between the segments and are not counted.
+    for (const char *k : {"k1", "k1_esup", "k1_esuel", "k1_faces", "k1_fsup", "k1_geom"}) c->timings[k] = 0.f;
+    int *d_mx = c->counters;  // [0] = mx_epp, [1] = mx_fpp, [2] = boundary faces
     NPB_CUDA(cudaMemsetAsync(d_mx, 0, sizeof(int) * 8, s));
 
     // ---- esup ----
-    int32_t *cursor = nullptr;
+    int32_t *cursor = nullptr, *fbase = nullptr;
+    NPB_TRY(npb_alloc(c, (void **)&c->esup_ptr, sizeof(int32_t) * (np + 1)));
+    NPB_TRY(npb_alloc(c, (void **)&c->esuel, sizeof(int32_t) * ne * sfe));
+    NPB_TRY(npb_alloc(c, (void **)&c->infael, sizeof(int32_t) * ne * sfe));
+    NPB_TRY(npb_alloc(c, (void **)&c->bpoint, (size_t)np));
+    NPB_TRY(npb_alloc(c, (void **)&c->fsup_ptr, sizeof(int32_t) * (np + 1)));
+    NPB_CUDA(cudaMalloc(&cursor, sizeof(int32_t) * (np + 1)));
+    NPB_CUDA(cudaMalloc(&fbase, sizeof(int32_t) * (ne + 1)));
     {
-        NpbTimer tm(c, "k1_esup");
-        NPB_TRY(npb_alloc(c, (void **)&c->esup_ptr, sizeof(int32_t) * (np + 1)));
-        NPB_CUDA(cudaMalloc(&cursor, sizeof(int32_t) * (np + 1)));
+        NpbTimer tm(c, "k1_esup", true);
         NPB_CUDA(cudaMemsetAsync(c->esup_ptr, 0, sizeof(int32_t) * (np + 1), s));
         k_count_nodes<<<npb_blocks(ne * spe, T), T, 0, s>>>(c->inpoel, ne * spe, c->esup_ptr);
         NPB_LAUNCH(c);
         NPB_TRY(npb_exclusive_scan_i32(c, c->esup_ptr, c->esup_ptr, np + 1));
+        tm.stop();
+    }
+    {
         int32_t total = 0;
         NPB_CUDA(cudaMemcpyAsync(&total, c->esup_ptr + np, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
         NPB_CUDA(cudaStreamSynchronize(s));
         c->len_esup = total;
         NPB_TRY(npb_alloc(c, (void **)&c->esup, sizeof(int32_t) * (size_t)(total > 0 ? total : 1)));
+    }
+    {
+        NpbTimer tm(c, "k1_esup", true);
         NPB_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (np + 1), s));
         k_fill_rows<<<npb_blocks(ne * spe, T), T, 0, s>>>(c->inpoel, ne * spe, spe, c->esup_ptr, cursor, c->esup);
         NPB_LAUNCH(c);
@@ -278,32 +305,45 @@ int npb_k1_build(npb_ctx *c, const i64 *h_conn, const i64 *h_types, const double
     }
     // ---- esuel ----
     {
-        NpbTimer tm(c, "k1_esuel");
-        NPB_TRY(npb_alloc(c, (void **)&c->esuel, sizeof(int32_t) * ne * sfe));
-        k_esuel<<<npb_blocks(ne * sfe, 128), 128, 0, s>>>(c->tab, c->inpoel, c->etype, c->esup_ptr, c->esup, ne, spe, sfe,
-                                                         c->esuel);
+        NpbTimer tm(c, "k1_esuel", true);
+        FaceMasks fm;
+        for (int t = 0; t < NPB_N_TYPES; t++)
+            for (int l = 0; l < NPB_MX_FE; l++) {
+                unsigned char m = 0;
+                for (int k = 0; k < c->tab.lnofa[t][l]; k++) m |= (unsigned char)(1u << c->tab.lpofa[t][l][k]);
+                fm.m[t][l] = l < c->tab.nfael[t] ? m : 0;
+            }
+        if (spe == 4)
+            k_esuel<4><<<npb_blocks(ne * sfe, 256), 256, 0, s>>>(c->tab, fm, c->inpoel, c->etype, c->esup_ptr, c->esup, ne, sfe, c->esuel);
+        else
+            k_esuel<8><<<npb_blocks(ne * sfe, 256), 256, 0, s>>>(c->tab, fm, c->inpoel, c->etype, c->esup_ptr, c->esup, ne, sfe, c->esuel);
         NPB_LAUNCH(c);
         tm.stop();
     }
     // ---- faces: numbering, inpofa, esuf, tags, fsup histogram ----
-    int32_t *fbase = nullptr;
     {
-        NpbTimer tm(c, "k1_faces");
-        NPB_CUDA(cudaMalloc(&fbase, sizeof(int32_t) * (ne + 1)));
+        NpbTimer tm(c, "k1_faces", true);
         k_owner_count<<<npb_blocks(ne + 1, T), T, 0, s>>>(c->tab, c->etype, c->esuel, ne, sfe, fbase);
         NPB_LAUNCH(c);
         NPB_TRY(npb_exclusive_scan_i32(c, fbase, fbase, ne + 1));
+        tm.stop();
+    }
+    {
         int32_t nfaces = 0;
         NPB_CUDA(cudaMemcpyAsync(&nfaces, fbase + ne, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
         NPB_CUDA(cudaStreamSynchronize(s));
         c->n_faces = nfaces;
         size_t nf1 = (size_t)(nfaces > 0 ? nfaces : 1);
-        NPB_TRY(npb_alloc(c, (void **)&c->infael, sizeof(int32_t) * ne * sfe));
         NPB_TRY(npb_alloc(c, (void **)&c->inpofa, sizeof(int32_t) * nf1 * NPB_MX_PF));
         NPB_TRY(npb_alloc(c, (void **)&c->esuf2, sizeof(int2) * nf1));
         NPB_TRY(npb_alloc(c, (void **)&c->bface, nf1));
-        NPB_TRY(npb_alloc(c, (void **)&c->bpoint, (size_t)np));
-        NPB_TRY(npb_alloc(c, (void **)&c->fsup_ptr, sizeof(int32_t) * (np + 1)));
+        NPB_TRY(npb_alloc(c, (void **)&c->centroids, sizeof(double) * ne * 3));
+        NPB_TRY(npb_alloc(c, (void **)&c->fcent, sizeof(double) * nf1 * 3));
+        NPB_TRY(npb_alloc(c, (void **)&c->fnormal, sizeof(double) * nf1 * 3));
+        NPB_TRY(npb_alloc(c, (void **)&c->farea, sizeof(double) * nf1));
+    }
+    {
+        NpbTimer tm(c, "k1_faces", true);
         NPB_CUDA(cudaMemsetAsync(c->bpoint, 0, (size_t)np, s));
         NPB_CUDA(cudaMemsetAsync(c->fsup_ptr, 0, sizeof(int32_t) * (np + 1), s));
         k_faces<<<npb_blocks(ne, 128), 128, 0, s>>>(c->tab, c->inpoel, c->etype, c->esuel, fbase, ne, spe, sfe, c->infael,
@@ -313,13 +353,19 @@ int npb_k1_build(npb_ctx *c, const i64 *h_conn, const i64 *h_types, const double
     }
     // ---- fsup ----
     {
-        NpbTimer tm(c, "k1_fsup");
+        NpbTimer tm(c, "k1_fsup", true);
         NPB_TRY(npb_exclusive_scan_i32(c, c->fsup_ptr, c->fsup_ptr, np + 1));
+        tm.stop();
+    }
+    {
         int32_t total = 0;
         NPB_CUDA(cudaMemcpyAsync(&total, c->fsup_ptr + np, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
         NPB_CUDA(cudaStreamSynchronize(s));
         c->len_fsup = total;
         NPB_TRY(npb_alloc(c, (void **)&c->fsup, sizeof(int32_t) * (size_t)(total > 0 ? total : 1)));
+    }
+    {
+        NpbTimer tm(c, "k1_fsup", true);
         NPB_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (np + 1), s));
         k_fill_fsup<<<npb_blocks(c->n_faces * NPB_MX_PF, T), T, 0, s>>>(c->inpofa, c->n_faces, c->fsup_ptr, cursor, c->fsup);
         NPB_LAUNCH(c);
@@ -339,6 +385,6 @@ int npb_k1_build(npb_ctx *c, const i64 *h_conn, const i64 *h_types, const double
     NPB_CUDA(cudaFree(fbase));
     // ---- geometry (k1_geometry.cu, compiled without FMA contraction) ----
     NPB_TRY(npb_k1_geometry(c));
-    tk1.stop();
+    for (const char *k : {"k1_esup", "k1_esuel", "k1_faces", "k1_fsup", "k1_geom"}) c->timings["k1"] += c->timings[k];
     return NPB_OK;
 }

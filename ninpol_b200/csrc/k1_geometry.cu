@@ -108,12 +108,7 @@ int npb_k1_geometry(npb_ctx *c)
 {
     const int T = 256;
     cudaStream_t s = c->stream;
-    NpbTimer tm(c, "k1_geom");
-    size_t nf1 = (size_t)(c->n_faces > 0 ? c->n_faces : 1);
-    NPB_TRY(npb_alloc(c, (void **)&c->centroids, sizeof(double) * c->n_elems * 3));
-    NPB_TRY(npb_alloc(c, (void **)&c->fcent, sizeof(double) * nf1 * 3));
-    NPB_TRY(npb_alloc(c, (void **)&c->fnormal, sizeof(double) * nf1 * 3));
-    NPB_TRY(npb_alloc(c, (void **)&c->farea, sizeof(double) * nf1));
+    NpbTimer tm(c, "k1_geom");   // outputs were allocated by npb_k1_build
     k_centroids<<<npb_blocks(c->n_elems, T), T, 0, s>>>(c->tab, c->inpoel, c->etype, c->coords, c->n_elems, c->spe, c->dim,
                                                        c->centroids);
     NPB_LAUNCH(c);
