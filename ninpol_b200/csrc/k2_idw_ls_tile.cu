@@ -21,7 +21,7 @@
 
 #define TILE_NB 64
 #define TILE_T 256
-#define IDW_ECAP 3072
+#define IDW_ECAP 1536
 #define LS_ECAP 1408
 #define IDW_EPS ((double)1.0000000036274937e-15f) /* float32(1e-15), idw.pyx:53 */
 
@@ -58,7 +58,7 @@ struct TileArgs {
     int direct;          // 1: write the CSR at indptr[] positions and count exact zeros; 0: two-pass mode
 };
 
-__global__ void __launch_bounds__(TILE_T) k_idw_tile(TileArgs a)
+__global__ void __launch_bounds__(TILE_T, 7) k_idw_tile(TileArgs a)
 {
     __shared__ double s_r[IDW_ECAP + TILE_NB];
     __shared__ int s_e[IDW_ECAP];
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(TILE_T) k_idw_tile(TileArgs a)
 #define S2(a, b) __dsub_rn(a, b)
 #define A2(a, b) __dadd_rn(a, b)
 
-__global__ void __launch_bounds__(TILE_T) k_ls_tile(TileArgs a)
+__global__ void __launch_bounds__(TILE_T, 5) k_ls_tile(TileArgs a)
 {
     __shared__ double s_vx[LS_ECAP + TILE_NB], s_vy[LS_ECAP + TILE_NB], s_vz[LS_ECAP + TILE_NB];
     __shared__ int s_e[LS_ECAP];
@@ -293,7 +293,7 @@ static void tile_args(npb_ctx *c, TileArgs &a, int method, i64 lo, i64 hi, int d
 static int tile_launch(npb_ctx *c, const TileArgs &a, int method)
 {
     i64 ntiles = (a.p_hi - a.p_lo + a.nb - 1) / a.nb;
-    int grid = (int)(ntiles < (i64)c->sm_count * 5 ? ntiles : (i64)c->sm_count * 5);
+    int grid = (int)(ntiles < (i64)c->sm_count * 8 ? ntiles : (i64)c->sm_count * 8);
     if (grid < 1) return NPB_OK;
     NpbTimer tm(c, "k2_main");
     if (method == NPB_METHOD_IDW)
