@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <thread>
 #include "common.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -70,6 +71,100 @@ void NpbTimer::stop()
     a = b = nullptr;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Host <-> device copies for PAGEABLE caller memory (numpy arrays): staged through two page-locked
+// buffers, the host-side memcpy of chunk i+1 (split over a few threads) overlapping the DMA of chunk i.
+// cudaMemcpy on pageable memory does the same staging single-threaded at 6-10 GB/s; this reaches the
+// PCIe rate.  Page-locked caller memory (npb_host_alloc) is detected and copied directly.
+// ------------------------------------------------------------------------------------------------
+#define NPB_STAGE_BYTES ((size_t)32 << 20)
+#define NPB_STAGE_THREADS 4
+
+static void par_memcpy(void *dst, const void *src, size_t n)
+{
+    if (n < ((size_t)4 << 20)) {
+        memcpy(dst, src, n);
+        return;
+    }
+    std::thread th[NPB_STAGE_THREADS];
+    size_t part = (n + NPB_STAGE_THREADS - 1) / NPB_STAGE_THREADS;
+    part = (part + 4095) & ~(size_t)4095;
+    for (int t = 0; t < NPB_STAGE_THREADS; t++) {
+        size_t b = (size_t)t * part;
+        size_t len = b >= n ? 0 : (n - b < part ? n - b : part);
+        th[t] = std::thread([=]() {
+            if (len) memcpy((char *)dst + b, (const char *)src + b, len);
+        });
+    }
+    for (int t = 0; t < NPB_STAGE_THREADS; t++) th[t].join();
+}
+
+static bool is_pinned(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+static int ensure_stage(npb_ctx *c)
+{
+    for (int i = 0; i < 2; i++)
+        if (!c->stage[i]) {
+            NPB_CUDA(cudaHostAlloc(&c->stage[i], NPB_STAGE_BYTES, cudaHostAllocDefault));
+            NPB_CUDA(cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming));
+        }
+    return NPB_OK;
+}
+
+int npb_h2d(npb_ctx *c, void *dst_dev, const void *src_host, size_t bytes)
+{
+    if (bytes == 0) return NPB_OK;
+    if (bytes < ((size_t)8 << 20) || is_pinned(src_host)) {
+        NPB_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, c->stream));
+        return NPB_OK;
+    }
+    NPB_TRY(ensure_stage(c));
+    int k = 0;
+    for (size_t off = 0; off < bytes; off += NPB_STAGE_BYTES, k ^= 1) {
+        size_t n = bytes - off < NPB_STAGE_BYTES ? bytes - off : NPB_STAGE_BYTES;
+        NPB_CUDA(cudaEventSynchronize(c->stage_ev[k]));   // the DMA that last read this buffer is done
+        par_memcpy(c->stage[k], (const char *)src_host + off, n);
+        NPB_CUDA(cudaMemcpyAsync((char *)dst_dev + off, c->stage[k], n, cudaMemcpyHostToDevice, c->stream));
+        NPB_CUDA(cudaEventRecord(c->stage_ev[k], c->stream));
+    }
+    return NPB_OK;
+}
+
+// blocking: returns when dst_host holds the data
+int npb_d2h(npb_ctx *c, void *dst_host, const void *src_dev, size_t bytes)
+{
+    if (bytes == 0) return NPB_OK;
+    if (bytes < ((size_t)8 << 20) || is_pinned(dst_host)) {
+        NPB_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+        NPB_CUDA(cudaStreamSynchronize(c->stream));
+        return NPB_OK;
+    }
+    NPB_TRY(ensure_stage(c));
+    size_t nchunks = (bytes + NPB_STAGE_BYTES - 1) / NPB_STAGE_BYTES;
+    for (size_t i = 0; i <= nchunks; i++) {
+        if (i < nchunks) {   // start the DMA of chunk i
+            size_t off = i * NPB_STAGE_BYTES, n = bytes - off < NPB_STAGE_BYTES ? bytes - off : NPB_STAGE_BYTES;
+            NPB_CUDA(cudaMemcpyAsync(c->stage[i & 1], (const char *)src_dev + off, n, cudaMemcpyDeviceToHost, c->stream));
+            NPB_CUDA(cudaEventRecord(c->stage_ev[i & 1], c->stream));
+        }
+        if (i > 0) {         // drain chunk i-1 while chunk i is in flight
+            size_t off = (i - 1) * NPB_STAGE_BYTES, n = bytes - off < NPB_STAGE_BYTES ? bytes - off : NPB_STAGE_BYTES;
+            NPB_CUDA(cudaEventSynchronize(c->stage_ev[(i - 1) & 1]));
+            par_memcpy((char *)dst_host + off, c->stage[(i - 1) & 1], n);
+        }
+    }
+    return NPB_OK;
+}
+
 int npb_comm_destroy(npb_ctx *c);
 int npb_psup_stats(npb_ctx *c);
 
@@ -78,7 +173,9 @@ static void free_mesh(npb_ctx *c)
     for (void *p : c->owned) cudaFree(p);
     c->owned.clear();
     c->inpoel = c->esup_ptr = c->esup = c->esuel = c->infael = c->inpofa = c->fsup_ptr = c->fsup = nullptr;
-    c->psup_ptr = c->psup = c->inedel = c->inpoed = c->node_list = nullptr;
+    c->psup_ptr = c->psup = c->node_list = nullptr;
+    c->inedel_d = c->inpoed_d = nullptr;
+    c->n_edges = 0;
     c->etype = c->bface = c->bpoint = c->nflag = nullptr;
     c->esuf2 = nullptr;
     c->coords = c->centroids = c->fcent = c->fnormal = c->farea = c->perm = c->diff_mag = c->neumann = nullptr;
@@ -137,6 +234,10 @@ extern "C" int npb_destroy(npb_ctx *c)
     if (c->scratch) cudaFree(c->scratch);
     if (c->gls_ws) cudaFree(c->gls_ws);
     if (c->counters) cudaFree(c->counters);
+    for (int i = 0; i < 2; i++) {
+        if (c->stage[i]) cudaFreeHost(c->stage[i]);
+        if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
+    }
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_b) cudaEventDestroy(c->ev_b);
     cudaStreamDestroy(c->stream);
@@ -329,7 +430,7 @@ extern "C" int npb_set_cell_field(npb_ctx *c, const char *name, const double *da
             return NPB_ERR_ARG;
         }
         if (!c->perm) NPB_TRY(npb_alloc(c, (void **)&c->perm, sizeof(double) * n));
-        NPB_CUDA(cudaMemcpyAsync(c->perm, data, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+        NPB_TRY(npb_h2d(c, c->perm, data, sizeof(double) * n));
         c->have_perm = true;
     } else if (strcmp(name, "diff_mag") == 0) {
         if (n != c->n_elems) {
@@ -337,7 +438,7 @@ extern "C" int npb_set_cell_field(npb_ctx *c, const char *name, const double *da
             return NPB_ERR_ARG;
         }
         if (!c->diff_mag) NPB_TRY(npb_alloc(c, (void **)&c->diff_mag, sizeof(double) * n));
-        NPB_CUDA(cudaMemcpyAsync(c->diff_mag, data, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+        NPB_TRY(npb_h2d(c, c->diff_mag, data, sizeof(double) * n));
         c->have_dm = true;
     } else {
         npb_set_error("npb_set_cell_field: unknown field '%s'", name);
@@ -368,7 +469,7 @@ extern "C" int npb_set_point_flags(npb_ctx *c, const int64_t *flag, int64_t n_po
     NPB_CUDA(cudaSetDevice(c->device));
     i64 *tmp = nullptr;
     NPB_CUDA(cudaMalloc(&tmp, sizeof(i64) * n_points));
-    NPB_CUDA(cudaMemcpyAsync(tmp, flag, sizeof(i64) * n_points, cudaMemcpyHostToDevice, c->stream));
+    NPB_TRY(npb_h2d(c, tmp, flag, sizeof(i64) * n_points));
     k_flags<<<npb_blocks(n_points, 256), 256, 0, c->stream>>>(tmp, n_points, c->nflag);
     NPB_LAUNCH(c);
     NPB_CUDA(cudaStreamSynchronize(c->stream));
@@ -496,10 +597,10 @@ extern "C" int npb_interpolate_fetch(npb_ctx *c, int32_t *indptr, int32_t *indic
     }
     {
         NpbTimer tm(c, "d2h_csr");
-        if (indptr) NPB_CUDA(cudaMemcpyAsync(indptr, c->indptr, sizeof(int32_t) * (c->n_points + 1), cudaMemcpyDeviceToHost, s));
-        if (indices && c->nnz > 0) NPB_CUDA(cudaMemcpyAsync(indices, c->indices, sizeof(int32_t) * c->nnz, cudaMemcpyDeviceToHost, s));
-        if (data && c->nnz > 0) NPB_CUDA(cudaMemcpyAsync(data, c->data, sizeof(double) * c->nnz, cudaMemcpyDeviceToHost, s));
-        if (neumann) NPB_CUDA(cudaMemcpyAsync(neumann, c->neumann, sizeof(double) * c->n_points, cudaMemcpyDeviceToHost, s));
+        if (indptr) NPB_TRY(npb_d2h(c, indptr, c->indptr, sizeof(int32_t) * (c->n_points + 1)));
+        if (indices && c->nnz > 0) NPB_TRY(npb_d2h(c, indices, c->indices, sizeof(int32_t) * c->nnz));
+        if (data && c->nnz > 0) NPB_TRY(npb_d2h(c, data, c->data, sizeof(double) * c->nnz));
+        if (neumann) NPB_TRY(npb_d2h(c, neumann, c->neumann, sizeof(double) * c->n_points));
         tm.stop();
     }
     NPB_CUDA(cudaStreamSynchronize(s));

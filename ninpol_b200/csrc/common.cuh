@@ -78,7 +78,7 @@ struct npb_ctx {
     uint8_t *bface = nullptr, *bpoint = nullptr;
     int32_t *fsup_ptr = nullptr, *fsup = nullptr;
     int32_t *psup_ptr = nullptr, *psup = nullptr;
-    int32_t *inedel = nullptr, *inpoed = nullptr;
+    i64 *inedel_d = nullptr, *inpoed_d = nullptr;   // edges, reference layout (int64), built when build_edges
     double *centroids = nullptr, *fcent = nullptr, *fnormal = nullptr, *farea = nullptr;
 
     // ---- per-variable inputs ----
@@ -116,11 +116,15 @@ struct npb_ctx {
     size_t gls_ws_cap = 0;
     int *counters = nullptr;     // small device int array (work counters, flags)
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;  // npb_timer_start / stop
+    void *stage[2] = {nullptr, nullptr};         // page-locked staging buffers for pageable host memory
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
 };
 
 // ---- helpers implemented in capi.cu ----
 int npb_alloc(npb_ctx *c, void **p, size_t bytes, bool owned_by_mesh = true);
 int npb_ensure(void **p, size_t *cap, size_t bytes);
+int npb_h2d(npb_ctx *c, void *dst_dev, const void *src_host, size_t bytes);
+int npb_d2h(npb_ctx *c, void *dst_host, const void *src_dev, size_t bytes);
 struct NpbTimer {
     npb_ctx *c;
     const char *name;
@@ -134,6 +138,8 @@ struct NpbTimer {
 int npb_exclusive_scan_i32(npb_ctx *c, const int32_t *in, int32_t *out, i64 n);   // out may alias in
 int npb_max_i32(npb_ctx *c, const int32_t *in, i64 n, int32_t *host_out);
 int npb_select_class(npb_ctx *c, const uint8_t *cls, i64 lo, i64 hi, int which, int32_t *out, int *host_count);
+int npb_sort_pairs_u32(npb_ctx *c, const uint32_t *keys_in, uint32_t *keys_out, const uint32_t *vals_in, uint32_t *vals_out, i64 n);
+int npb_propagate_heads(npb_ctx *c, uint2 *pairs, i64 n);
 
 // ---- kernels' host drivers ----
 int npb_k1_build(npb_ctx *c, const i64 *h_conn, const i64 *h_types, const double *h_coords);

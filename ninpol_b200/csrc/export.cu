@@ -72,6 +72,8 @@ __global__ void k_psup(ElemTables tab, const int32_t *__restrict__ inpoel, const
     }
 }
 
+static int out_i64(npb_ctx *c, const i64 *dev, i64 n, void *out, i64 cap);
+
 static int build_psup(npb_ctx *c)
 {
     if (c->psup_ptr) return NPB_OK;
@@ -105,11 +107,150 @@ static int build_psup(npb_ctx *c)
     return NPB_OK;
 }
 
+
+// ---- edges: Grid.build_inedel, grid.pyx:527-580 -------------------------------------------------
+// The reference numbers edges in first-encounter order over (element, local edge) and identifies an
+// edge by the 32-bit truncation of myhash(sorted end points) (grid.pyx:29-43, unordered_map[int,int]
+// at :539), so two edges whose hashes collide share one id.  Device restatement: hash every (e, j),
+// stable radix sort of (hash, slot) pairs -> the head of each run is the first encounter; an exclusive
+// scan of the head flags IN SLOT ORDER gives the first-encounter numbering; the head's id is copied
+// down its run.  Bit-identical to the serial loop, collisions included.
+__device__ __forceinline__ unsigned ref_myhash2_lo32(int a, int b)
+{
+    unsigned long long seed = 2ull;
+    int v[2] = {a, b};
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        int x = v[i];
+        x = (int)((unsigned)((x >> 16) ^ x) * 0x45d9f3bu);
+        x = (int)((unsigned)((x >> 16) ^ x) * 0x45d9f3bu);
+        x = (x >> 16) ^ x;
+        seed ^= (unsigned long long)((unsigned)x + 0x9e3779b9u) + (seed << 6) + (seed >> 2);
+    }
+    return (unsigned)seed;
+}
+
+__global__ void k_edge_count(EdgeTables et, const uint8_t *__restrict__ etype, i64 n_elems, int32_t *__restrict__ cnt)
+{
+    i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e > n_elems) return;
+    cnt[e] = e == n_elems ? 0 : et.nedel[etype[e]];
+}
+
+__global__ void k_edge_keys(EdgeTables et, const int32_t *__restrict__ inpoel, const uint8_t *__restrict__ etype,
+                            const int32_t *__restrict__ ebase, i64 n_elems, int spe, uint32_t *__restrict__ keys,
+                            uint32_t *__restrict__ slots)
+{
+    i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_elems * NPB_MX_EE) return;
+    i64 e = idx / NPB_MX_EE;
+    int j = (int)(idx - e * NPB_MX_EE);
+    int t = etype[e];
+    if (j >= et.nedel[t]) return;
+    int a = inpoel[e * spe + et.lpoed[t][j][0]], b = inpoel[e * spe + et.lpoed[t][j][1]];
+    int s0 = a < b ? a : b, s1 = a < b ? b : a;
+    i64 q = (i64)ebase[e] + j;
+    keys[q] = ref_myhash2_lo32(s0, s1);
+    slots[q] = (uint32_t)idx;
+}
+
+// sorted order: head flags, and the same flags scattered to slot order (as 0/1 for the numbering scan)
+__global__ void k_edge_heads(const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ sslots, i64 n,
+                             uint2 *__restrict__ pairs, int32_t *__restrict__ first_at_slot)
+{
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool head = (i == 0) || (skeys[i] != skeys[i - 1]);
+    pairs[i] = make_uint2(head ? 1u : 0u, sslots[i]);
+    if (head) first_at_slot[sslots[i]] = 1;
+}
+
+__global__ void k_edge_emit(const uint2 *__restrict__ pairs, const uint32_t *__restrict__ sslots, i64 n,
+                            const int32_t *__restrict__ number_at_slot, EdgeTables et, const int32_t *__restrict__ inpoel,
+                            const uint8_t *__restrict__ etype, int spe, i64 *__restrict__ inedel, i64 *__restrict__ inpoed)
+{
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t head_slot = pairs[i].y, slot = sslots[i];
+    int id = number_at_slot[head_slot];
+    inedel[slot] = id;
+    if (slot == head_slot) {
+        i64 e = slot / NPB_MX_EE;
+        int j = (int)(slot - e * NPB_MX_EE);
+        int t = etype[e];
+        inpoed[(i64)id * 2 + 0] = inpoel[e * spe + et.lpoed[t][j][0]];
+        inpoed[(i64)id * 2 + 1] = inpoel[e * spe + et.lpoed[t][j][1]];
+    }
+}
+
+__global__ void k_fill_i64(i64 *p, i64 n, i64 v)
+{
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// builds c->inedel_d [n_elems,12] and c->inpoed_d [n_edges,2] (int64, reference layout) once
+static int build_edges(npb_ctx *c)
+{
+    if (c->inedel_d) return NPB_OK;
+    cudaStream_t s = c->stream;
+    i64 ne = c->n_elems, nslots = ne * NPB_MX_EE;
+    if (nslots >= (1ll << 31)) {
+        npb_set_error("edge table too large for 32-bit slots");
+        return NPB_ERR_RANGE;
+    }
+    int32_t *ebase = nullptr, *flag = nullptr;
+    uint32_t *keys = nullptr, *slots = nullptr, *skeys = nullptr, *sslots = nullptr;
+    uint2 *pairs = nullptr;
+    NPB_CUDA(cudaMalloc(&ebase, sizeof(int32_t) * (ne + 1)));
+    k_edge_count<<<npb_blocks(ne + 1, 256), 256, 0, s>>>(c->etab, c->etype, ne, ebase);
+    NPB_LAUNCH(c);
+    NPB_TRY(npb_exclusive_scan_i32(c, ebase, ebase, ne + 1));
+    int32_t total = 0;
+    NPB_CUDA(cudaMemcpyAsync(&total, ebase + ne, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    NPB_CUDA(cudaStreamSynchronize(s));
+    size_t n1 = (size_t)(total > 0 ? total : 1);
+    NPB_CUDA(cudaMalloc(&keys, 4 * n1));
+    NPB_CUDA(cudaMalloc(&slots, 4 * n1));
+    NPB_CUDA(cudaMalloc(&skeys, 4 * n1));
+    NPB_CUDA(cudaMalloc(&sslots, 4 * n1));
+    NPB_CUDA(cudaMalloc(&pairs, 8 * n1));
+    NPB_CUDA(cudaMalloc(&flag, sizeof(int32_t) * (size_t)(nslots + 1)));
+    NPB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t) * (size_t)(nslots + 1), s));
+    NPB_TRY(npb_alloc(c, (void **)&c->inedel_d, sizeof(i64) * (size_t)nslots));
+    k_fill_i64<<<npb_blocks(nslots, 256), 256, 0, s>>>(c->inedel_d, nslots, -1);
+    NPB_LAUNCH(c);
+    if (total > 0) {
+        k_edge_keys<<<npb_blocks(nslots, 256), 256, 0, s>>>(c->etab, c->inpoel, c->etype, ebase, ne, c->spe, keys, slots);
+        NPB_LAUNCH(c);
+        NPB_TRY(npb_sort_pairs_u32(c, keys, skeys, slots, sslots, total));
+        k_edge_heads<<<npb_blocks(total, 256), 256, 0, s>>>(skeys, sslots, total, pairs, flag);
+        NPB_LAUNCH(c);
+        NPB_TRY(npb_propagate_heads(c, pairs, total));
+        NPB_TRY(npb_exclusive_scan_i32(c, flag, flag, nslots + 1));
+    }
+    int32_t n_edges = 0;
+    NPB_CUDA(cudaMemcpyAsync(&n_edges, flag + nslots, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    NPB_CUDA(cudaStreamSynchronize(s));
+    c->n_edges = n_edges;
+    NPB_TRY(npb_alloc(c, (void **)&c->inpoed_d, sizeof(i64) * 2 * (size_t)(n_edges > 0 ? n_edges : 1)));
+    if (total > 0) {
+        k_edge_emit<<<npb_blocks(total, 256), 256, 0, s>>>(pairs, sslots, total, flag, c->etab, c->inpoel, c->etype, c->spe,
+                                                          c->inedel_d, c->inpoed_d);
+        NPB_LAUNCH(c);
+    }
+    NPB_CUDA(cudaStreamSynchronize(s));
+    cudaFree(ebase); cudaFree(flag); cudaFree(keys); cudaFree(slots); cudaFree(skeys); cudaFree(sslots); cudaFree(pairs);
+    return NPB_OK;
+}
+
+int npb_edges_stats(npb_ctx *c) { return c->build_edges ? build_edges(c) : NPB_OK; }
+
 int npb_k1_extras(npb_ctx *c)
 {
-    // psup is built on first use (npb_export_array / npb_psup_stats); edges: see DESIGN.md, "next" row
-    (void)c;
-    return NPB_OK;
+    // psup is built on first use (npb_export_array / npb_psup_stats); edges at load time when asked for,
+    // like the reference (grid.pyx:219-227)
+    return c->build_edges ? build_edges(c) : NPB_OK;
 }
 
 int npb_psup_stats(npb_ctx *c)
@@ -169,6 +310,15 @@ int npb_export_array(npb_ctx *c, const char *name, void *out, i64 cap)
     if (!strcmp(name, "esup_ptr")) return export_rows(c, c->esup_ptr, np + 1, 1, 1, out, cap);
     if (!strcmp(name, "fsup")) return export_rows(c, c->fsup, c->len_fsup, 1, 1, out, cap);
     if (!strcmp(name, "fsup_ptr")) return export_rows(c, c->fsup_ptr, np + 1, 1, 1, out, cap);
+    if (!strcmp(name, "inedel") || !strcmp(name, "inpoed")) {
+        if (!c->build_edges) {
+            npb_set_error("edge structures were not requested (build_edges = 0)");
+            return NPB_ERR_STATE;
+        }
+        NPB_TRY(build_edges(c));
+        i64 n = !strcmp(name, "inedel") ? c->n_elems * NPB_MX_EE : c->n_edges * 2;
+        return out_i64(c, !strcmp(name, "inedel") ? c->inedel_d : c->inpoed_d, n, out, cap);
+    }
     if (!strcmp(name, "psup") || !strcmp(name, "psup_ptr")) {
         NPB_TRY(build_psup(c));
         if (!strcmp(name, "psup")) return export_rows(c, c->psup, c->len_psup, 1, 1, out, cap);

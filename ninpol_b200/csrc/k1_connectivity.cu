@@ -251,12 +251,12 @@ int npb_k1_build(npb_ctx *c, const i64 *h_conn, const i64 *h_types, const double
         i64 *d_conn = nullptr, *d_types = nullptr;
         NPB_CUDA(cudaMalloc(&d_conn, sizeof(i64) * ne * NPB_MX_PE));
         NPB_CUDA(cudaMalloc(&d_types, sizeof(i64) * ne));
-        NPB_CUDA(cudaMemcpyAsync(d_conn, h_conn, sizeof(i64) * ne * NPB_MX_PE, cudaMemcpyHostToDevice, s));
-        NPB_CUDA(cudaMemcpyAsync(d_types, h_types, sizeof(i64) * ne, cudaMemcpyHostToDevice, s));
+        NPB_TRY(npb_h2d(c, d_conn, h_conn, sizeof(i64) * ne * NPB_MX_PE));
+        NPB_TRY(npb_h2d(c, d_types, h_types, sizeof(i64) * ne));
         NPB_TRY(npb_alloc(c, (void **)&c->inpoel, sizeof(int32_t) * ne * spe));
         NPB_TRY(npb_alloc(c, (void **)&c->etype, ne));
         NPB_TRY(npb_alloc(c, (void **)&c->coords, sizeof(double) * np * 3));
-        NPB_CUDA(cudaMemcpyAsync(c->coords, h_coords, sizeof(double) * np * 3, cudaMemcpyHostToDevice, s));
+        NPB_TRY(npb_h2d(c, c->coords, h_coords, sizeof(double) * np * 3));
         k_convert_conn<<<npb_blocks(ne * spe, T), T, 0, s>>>(d_conn, d_types, ne, spe, c->inpoel, c->etype);
         NPB_LAUNCH(c);
         tm.stop();

@@ -2,6 +2,7 @@
 // library; the only translation unit that instantiates CUB, to keep build times down).
 // These are the "scan" steps of the counting-sort / two-pass-emit formulations of K1 and K3.
 #include <cub/device/device_reduce.cuh>
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
@@ -58,5 +59,33 @@ int npb_select_class(npb_ctx *c, const uint8_t *cls, i64 lo, i64 hi, int which, 
     c->launches += 2;
     NPB_CUDA(cudaMemcpyAsync(host_count, d_num, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     NPB_CUDA(cudaStreamSynchronize(c->stream));
+    return NPB_OK;
+}
+
+// stable sort of (key, value) pairs by 32-bit key (CUB radix sort); outputs in keys_out / vals_out
+int npb_sort_pairs_u32(npb_ctx *c, const uint32_t *keys_in, uint32_t *keys_out, const uint32_t *vals_in, uint32_t *vals_out, i64 n)
+{
+    if (n <= 0) return NPB_OK;
+    size_t need = 0;
+    NPB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, keys_in, keys_out, vals_in, vals_out, (int)n, 0, 32, c->stream));
+    NPB_TRY(npb_ensure(&c->scratch, &c->scratch_cap, need));
+    NPB_CUDA(cub::DeviceRadixSort::SortPairs(c->scratch, need, keys_in, keys_out, vals_in, vals_out, (int)n, 0, 32, c->stream));
+    c->launches += 8;
+    return NPB_OK;
+}
+
+struct HeadCopy {   // segmented "copy the run head's value forward": (flag, value) pairs
+    __host__ __device__ uint2 operator()(const uint2 &a, const uint2 &b) const { return b.x ? b : make_uint2(a.x, a.y); }
+};
+
+// in/out: pairs (is_head, value); after the call every element carries the value of its run's head
+int npb_propagate_heads(npb_ctx *c, uint2 *pairs, i64 n)
+{
+    if (n <= 0) return NPB_OK;
+    size_t need = 0;
+    NPB_CUDA(cub::DeviceScan::InclusiveScan(nullptr, need, pairs, pairs, HeadCopy(), (int)n, c->stream));
+    NPB_TRY(npb_ensure(&c->scratch, &c->scratch_cap, need));
+    NPB_CUDA(cub::DeviceScan::InclusiveScan(c->scratch, need, pairs, pairs, HeadCopy(), (int)n, c->stream));
+    c->launches += 2;
     return NPB_OK;
 }

@@ -42,7 +42,10 @@ class Grid:
             "inpofa": ((nf, et.MAX_POINTS_PER_FACE), _I),
             "esup_ptr": ((np_ + 1,), _I), "fsup_ptr": ((np_ + 1,), _I), "psup_ptr": ((np_ + 1,), _I),
             "esuf_ptr": ((nf + 1,), _I), "boundary_faces": ((nf,), _I), "boundary_points": ((np_,), _I),
+            "inedel": ((ne, et.MAX_EDGES_PER_ELEMENT), _I),
         }
+        if name == "inpoed":
+            return ((s("n_edges"), et.MAX_POINTS_PER_EDGE), _I)
         if name in table:
             return table[name]
         if name in ("esup", "fsup", "esuf", "psup"):
@@ -54,10 +57,8 @@ class Grid:
             raise AttributeError(name)
         if name in Grid._SCALARS:
             return self._ctx.scalar(name)
-        if name in ("inpoed", "inedel"):
-            if not self.build_edges:
-                return np.zeros((0, 0), dtype=_I)   # grid.pyx:132-133
-            raise NotImplementedError("edge structures (build_edges=True) are not built on the device yet")
+        if name in ("inpoed", "inedel") and not self.build_edges:
+            return np.zeros((0, 0), dtype=_I)   # grid.pyx:132-133
         cache = self.__dict__["_cache"]
         if name not in cache:
             shape, dtype = self._shape(name)

@@ -197,7 +197,8 @@ def attach_fields(mesh, variable="u", seed=2, neumann_rate=0.5, hull_nodes=None,
     if hull_nodes is None:
         p = mesh.points
         lo, hi = p.min(axis=0), p.max(axis=0)
-        hull_nodes = np.any((p == lo) | (p == hi), axis=1)
+        live = hi > lo                      # a flat axis (2-D meshes with z = 0) is not a hull
+        hull_nodes = np.any(((p == lo) | (p == hi)) & live[None, :], axis=1)
     flag = np.zeros(npts, dtype=np.float64)
     pick = rng.random(npts) < neumann_rate
     flag[hull_nodes & pick] = 1.0
@@ -215,12 +216,40 @@ def attach_fields(mesh, variable="u", seed=2, neumann_rate=0.5, hull_nodes=None,
     return mesh
 
 
+def quad_plane(n, perturb=0.0, seed=0, triangles=False):
+    """2-D unit square: n^2 quadrilaterals, or 2 n^2 triangles (each quad split along its 0-2 diagonal), with
+    3-column coordinates (z = 0) as meshio delivers them.  Exercises the reference's dim == 2 branches
+    (faces are edges: interpolator.pyx:296-298, grid.pyx:787-806, ls.pyx:79-80,105-106)."""
+    g = np.arange(n + 1, dtype=np.float64) / n
+    j, i = np.meshgrid(g, g, indexing="ij")
+    pts = np.stack([i.ravel(), j.ravel(), np.zeros((n + 1) ** 2)], axis=1)
+    if perturb > 0.0:
+        rng = np.random.default_rng(seed)
+        idx = np.arange(n + 1)
+        inner = (idx > 0) & (idx < n)
+        jj, ii = np.meshgrid(inner, inner, indexing="ij")
+        mask = (ii & jj).ravel()
+        d = rng.uniform(-perturb / n, perturb / n, size=(len(pts), 2))
+        pts[mask, :2] += d[mask]
+    N1 = n + 1
+    r = np.arange(n, dtype=np.int64)
+    jj, ii = np.meshgrid(r, r, indexing="ij")
+    base = (ii + N1 * jj).ravel()
+    quads = base[:, None] + np.array([0, 1, 1 + N1, N1], dtype=np.int64)[None, :]
+    if not triangles:
+        return SimpleMesh(pts, [CellBlock("quad", quads)])
+    tris = quads[:, np.array([[0, 1, 2], [0, 2, 3]])].reshape(-1, 3)
+    return SimpleMesh(pts, [CellBlock("triangle", tris)])
+
+
 def make_case(kind, n, variable="u", seed=0, neumann_rate=0.5, perturb=None, **kw):
     """Convenience: mesh + fields.  kind in {'hex', 'tet', 'mixed'}."""
     if kind == "hex":
         mesh = hex_box(n, perturb=0.0 if perturb is None else perturb, seed=seed)
     elif kind == "tet":
         mesh = kuhn_tet_box(n, perturb=0.25 if perturb is None else perturb, seed=seed)
+    elif kind in ("quad2d", "tri2d"):
+        mesh = quad_plane(n, perturb=0.0 if perturb is None else perturb, seed=seed, triangles=(kind == "tri2d"))
     elif kind == "mixed":
         a = kw.get("a", max(1, n // 4))
         b = kw.get("b", max(a + 1, n // 2))

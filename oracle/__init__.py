@@ -73,6 +73,7 @@ def lib():
         _lib.orc_build_fsup.restype = ctypes.c_longlong
         _lib.orc_build_esuf.restype = ctypes.c_longlong
         _lib.orc_gls.restype = ctypes.c_int
+        _lib.orc_build_inedel.restype = ctypes.c_longlong
     return _lib
 
 
@@ -153,7 +154,7 @@ class OracleGrid:
     """Grid.build + load_point_coords + calculate_centroids + calculate_normal_faces
     (grid.pyx:142-231, 661-809) through the C restatement; attribute names follow grid.pxd:128-187."""
 
-    def __init__(self, dim, n_elems, n_points, conn, etype, coords, build_psup=True):
+    def __init__(self, dim, n_elems, n_points, conn, etype, coords, build_psup=True, build_edges=False):
         L = lib()
         self.dim, self.n_elems, self.n_points = dim, n_elems, n_points
         self.inpoel = np.ascontiguousarray(conn, dtype=np.int64)
@@ -200,6 +201,13 @@ class OracleGrid:
             _ll(n_elems), _ll(self.n_faces), _ll(n_points), _p(self.inpoel), _p(self.element_types), _p(self.nfael),
             _p(self.lnofa), _p(self.lpofa), _p(self.infael), _p(self.esuf_ptr), _p(self.esuf), _p(self.inpofa),
             _p(self.boundary_faces), _p(self.boundary_points)))
+        self.n_edges = 0
+        if build_edges:                                     # Grid.build_inedel, grid.pyx:527-580
+            self.inedel = np.empty((n_elems, 12), dtype=np.int64)
+            inpoed = np.empty((n_elems * 12, 2), dtype=np.int64)
+            self.n_edges = int(L.orc_build_inedel(_ll(n_elems), _p(self.inpoel), _p(self.element_types), _p(self.nedel),
+                                                  _p(self.lpoed), _p(self.inedel), _p(inpoed)))
+            self.inpoed = inpoed[:self.n_edges].copy()
         self.centroids = np.zeros((n_elems, 3), dtype=np.float64)
         self.faces_centers = np.zeros((self.n_faces, 3), dtype=np.float64)
         L.orc_centroids(_ll(dim), _ll(n_elems), _ll(self.n_faces), _p(self.inpoel), _p(self.element_types), _p(self.npoel),
@@ -226,10 +234,10 @@ class OracleInterpolator:
     def __init__(self):
         self.grid = None
 
-    def load_mesh(self, mesh_obj, build_psup=True):
+    def load_mesh(self, mesh_obj, build_psup=True, build_edges=False):
         dim, n_elems, n_points, conn, etype = process_mesh(mesh_obj)
         self.grid = OracleGrid(dim, n_elems, n_points, conn, etype, np.asarray(mesh_obj.points, dtype=np.float64),
-                               build_psup=build_psup)
+                               build_psup=build_psup, build_edges=build_edges)
         self.cells = {}
         cdd = mesh_obj.cell_data_dict if mesh_obj.cell_data else {}
         for var, by_type in cdd.items():                    # load_cell_data, :428-451

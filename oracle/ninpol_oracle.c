@@ -644,3 +644,64 @@ int orc_gls(i64 n_points, i64 MXE, i64 MXF, const i64 *esup_ptr, const i64 *esup
     free(nL1); free(nL2); free(nL); free(KsSv); free(KsSvb); free(A); free(B); free(work);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Grid.build_inedel — grid.pyx:527-580 with myhash (:29-43).  The reference keys its hash map by the
+ * hash VALUE of the sorted end points, truncated to a C int (unordered_map[int, int], :539): two
+ * different edges whose 32-bit hashes collide are merged into one edge id.  Reproduced as is.
+ * inedel [n_elems, 12] and inpoed [n_elems*12, 2] are set to -1 here; returns n_edges.
+ * ---------------------------------------------------------------------------------------------- */
+static size_t ref_myhash2(i64 a, i64 b)
+{
+    size_t seed = 2;                                    /* len(vec) */
+    i64 v[2] = {a, b};
+    for (int i = 0; i < 2; i++) {
+        int x = (int)v[i];
+        x = (int)((unsigned int)((x >> 16) ^ x) * 0x45d9f3bu);
+        x = (int)((unsigned int)((x >> 16) ^ x) * 0x45d9f3bu);
+        x = (x >> 16) ^ x;
+        seed ^= (unsigned int)((unsigned int)x + 0x9e3779b9u) + (seed << 6) + (seed >> 2);
+    }
+    return seed;
+}
+
+i64 orc_build_inedel(i64 n_elems, const i64 *inpoel, const i64 *etype, const i64 *nedel, const i64 *lpoed,
+                     i64 *inedel, i64 *inpoed)
+{
+    const int MXE = 12;
+    size_t cap = 64;
+    while (cap < (size_t)n_elems * MXE * 2) cap <<= 1;
+    int *keys = (int *)malloc(sizeof(int) * cap);
+    int *vals = (int *)malloc(sizeof(int) * cap);
+    unsigned char *used = (unsigned char *)calloc(cap, 1);
+    i64 n_edges = 0;
+    for (i64 i = 0; i < n_elems * MXE; i++) inedel[i] = -1;
+    for (i64 i = 0; i < n_elems * MXE * 2; i++) inpoed[i] = -1;
+    for (i64 i = 0; i < n_elems; i++) {
+        i64 t = etype[i];
+        for (i64 j = 0; j < nedel[t]; j++) {
+            i64 e0 = inpoel[i * MX_PE + lpoed[(t * MXE + j) * 2 + 0]];
+            i64 e1 = inpoel[i * MX_PE + lpoed[(t * MXE + j) * 2 + 1]];
+            i64 s0 = e0, s1 = e1;
+            if (e0 > e1) { s0 = e1; s1 = e0; }
+            int key = (int)ref_myhash2(s0, s1);        /* size_t -> int key of the map */
+            size_t h = ((size_t)(unsigned int)key * 0x9E3779B97F4A7C15ull) & (cap - 1);
+            while (used[h] && keys[h] != key) h = (h + 1) & (cap - 1);
+            i64 idx;
+            if (!used[h]) {
+                used[h] = 1;
+                keys[h] = key;
+                vals[h] = (int)n_edges;
+                idx = n_edges;
+                inpoed[idx * 2 + 0] = e0;
+                inpoed[idx * 2 + 1] = e1;
+                n_edges++;
+            } else {
+                idx = vals[h];
+            }
+            inedel[i * MXE + j] = idx;
+        }
+    }
+    free(keys); free(vals); free(used);
+    return n_edges;
+}

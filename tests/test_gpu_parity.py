@@ -20,6 +20,9 @@ CASES = [("tet", 7, {}), ("hex", 8, {}), ("mixed", 8, {"a": 2, "b": 4}), ("tet",
          ("hex", 6, {"perturb": 0.2}), ("mixed", 12, {"a": 3, "b": 6}), ("tet", 3, {}), ("hex", 1, {}), ("tet", 1, {})]
 
 
+CASES_2D = [("quad2d", 6, {}), ("tri2d", 6, {"perturb": 0.2}), ("quad2d", 9, {"perturb": 0.2}), ("tri2d", 12, {})]
+
+
 def _pair(kind, n, kw):
     import ninpol_b200
     import oracle
@@ -157,3 +160,44 @@ def test_fallback_kernels_agree(kind, n, kw, monkeypatch):
         else:
             assert np.array_equal(W.data, Wo.data, equal_nan=True)
             assert np.array_equal(nv, nvo)
+
+
+@pytest.mark.parametrize("kind,n,kw", CASES_2D)
+def test_2d_meshes_bit_exact(kind, n, kw):
+    """dim == 2: faces are edges (interpolator.pyx:296-298), 2-D normal branch (grid.pyx:787-806), LS
+    z-degenerate fix-up (ls.pyx:79-80,105-106).  GLS is not compared in 2-D: its system has all-zero
+    z-columns there and the reference returns whatever DGELS leaves for a singular matrix."""
+    I, O = _pair(kind, n, kw)
+    assert I.grid.dim == 2
+    for s_ in GRID_SCALARS:
+        assert getattr(I.grid, s_) == getattr(O.grid, s_), s_
+    for name in GRID_ARRAYS:
+        assert np.array_equal(np.asarray(getattr(I.grid, name)), np.asarray(getattr(O.grid, name))), name
+    for method in ("idw", "ls"):
+        W, nv = I.interpolate("u", method)
+        Wo, nvo = O.interpolate("u", method)
+        assert np.array_equal(W.indptr, Wo.indptr) and np.array_equal(W.indices, Wo.indices)
+        assert np.array_equal(W.data, Wo.data, equal_nan=True)
+        assert np.array_equal(nv, nvo)
+
+
+@pytest.mark.parametrize("kind,n,kw", [("tet", 6, {}), ("hex", 7, {}), ("mixed", 8, {"a": 2, "b": 4}), ("tri2d", 9, {}), ("tet", 24, {})])
+def test_edge_structures_bit_exact(kind, n, kw):
+    """build_edges=True: inedel / inpoed / n_edges (grid.pyx:527-580), hash-identity semantics included."""
+    import ninpol_b200
+    import oracle
+    from ninpol_b200 import meshgen
+    mesh = meshgen.make_case(kind, n, **kw)
+    I = ninpol_b200.Interpolator(build_edges=True)
+    I.load_mesh(mesh_obj=mesh)
+    O = oracle.OracleInterpolator().load_mesh(mesh, build_edges=True)
+    assert I.grid.n_edges == O.grid.n_edges
+    assert np.array_equal(np.asarray(I.grid.inedel), O.grid.inedel)
+    assert np.array_equal(np.asarray(I.grid.inpoed), O.grid.inpoed)
+    d = I.grid.get_data()
+    assert d["esup"].shape == (I.grid.n_points, I.grid.MX_ELEMENTS_PER_POINT) and d["n_edges"] == O.grid.n_edges
+    assert np.array_equal(d["psup"][d["psup"] >= 0], O.grid.psup)
+    # without build_edges the reference leaves (0, 0) arrays (grid.pyx:132-133)
+    J = ninpol_b200.Interpolator()
+    J.load_mesh(mesh_obj=mesh)
+    assert J.grid.inedel.shape == (0, 0) and J.grid.n_edges == 0

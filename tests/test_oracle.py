@@ -53,7 +53,7 @@ REF = oracle.load_reference()
 
 @pytest.mark.skipif(REF is None, reason="compiled reference (oracle/_ref) not built in this checkout")
 @pytest.mark.parametrize("kind,n,kw", [("tet", 6, {}), ("hex", 7, {}), ("mixed", 8, {"a": 2, "b": 4}), ("hex", 5, {"perturb": 0.2}),
-                                       ("tet", 1, {}), ("hex", 1, {})])
+                                       ("tet", 1, {}), ("hex", 1, {}), ("quad2d", 6, {}), ("tri2d", 6, {"perturb": 0.2})])
 def test_oracle_matches_compiled_reference(kind, n, kw):
     mesh = meshgen.make_case(kind, n, **kw)
     I = REF.Interpolator()
@@ -77,3 +77,15 @@ def test_release_build_diffusion_magnitude():
     dm = oracle.diffusion_magnitude(K)
     tr = K[:, 0] + K[:, 4] + K[:, 8]
     assert np.array_equal(dm, (1 - 3 / tr) ** 2)
+
+
+@pytest.mark.skipif(REF is None, reason="compiled reference (oracle/_ref) not built in this checkout")
+@pytest.mark.parametrize("kind,n,kw", [("tet", 5, {}), ("mixed", 8, {"a": 2, "b": 4}), ("tri2d", 7, {})])
+def test_oracle_edges_match_compiled_reference(kind, n, kw):
+    mesh = meshgen.make_case(kind, n, **kw)
+    I = REF.Interpolator(build_edges=True)
+    I.load_mesh(mesh_obj=oracle.to_reference_mesh(mesh))
+    O = oracle.OracleInterpolator().load_mesh(mesh, build_edges=True)
+    assert I.grid.n_edges == O.grid.n_edges
+    assert np.array_equal(np.asarray(I.grid.inedel), O.grid.inedel)
+    assert np.array_equal(np.asarray(I.grid.inpoed), O.grid.inpoed)
