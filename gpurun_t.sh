@@ -1,9 +1,10 @@
 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python bench.py --workload hex200 --steps 3 --warmup 3 --method ls --also idw --no-cpu 2> gpurun_out/bh.err > gpurun_out/bh.json; tail -1 gpurun_out/bh.err
-python bench.py --workload tet203 --steps 3 --warmup 3 --method ls --also idw --no-cpu 2> gpurun_out/bt.err > gpurun_out/bt.json; tail -1 gpurun_out/bt.err
+python bench.py --steps 2 --warmup 3 --also idw,ls 2> gpurun_out/c4.err > gpurun_out/c4.json
+tail -2 gpurun_out/c4.err
 python - <<'PY'
 import json
-for f in ("bh","bt"):
-    d=json.load(open(f"gpurun_out/{f}.json"))
-    print(f, "LS nodes/s %.3g ms %.3f kernel_ms %.3f frac %.3f | IDW %.3g ms %.3f frac %.3f | e2e %.3g" % (d["value"], d["ms_per_step"], d["roofline"]["kernel_ms"], d["roofline"]["frac"], d["also"]["idw"]["value"], d["also"]["idw"]["ms_per_step"], d["also"]["idw"]["roofline"]["frac"], d["e2e"]["value"]))
+d=json.load(open("gpurun_out/c4.json"))
+print("GLS %.4g nodes/s ms %.1f fp64frac %.3f e2e %.4g (%.0f ms) traffic %s" % (d["value"], d["ms_per_step"], d["roofline"]["fp64"]["frac"], d["e2e"]["value"], d["e2e"]["ms_per_step"], d["roofline"]["traffic"]))
+for m,v in d["also"].items(): print(m, "%.4g nodes/s ms %.2f k2 %.2f frac %.3f" % (v["value"], v["ms_per_step"], v["k2_ms"], v["roofline"]["frac"]))
+print(d["load_mesh"]["breakdown_ms"], "wall", d["load_mesh"]["wall_s"], "cpu", d.get("cpu_baseline",{}).get("value"))
 PY

@@ -354,7 +354,19 @@ extern "C" int npb_load_mesh(npb_ctx *c, int dim, int64_t n_elems, int64_t n_poi
                     c->etab.lpoed[t][e][k] = (int8_t)(v < 0 ? 0 : v);
                 }
         }
-        if (nfael[t] >= 0) {  // a type of this mesh dimension (interpolator.pyx:304-305)
+    }
+    // device row strides from the element types that are actually present in the mesh
+    bool present[NPB_N_TYPES] = {false, false, false, false, false, false, false, false};
+    for (int64_t e = 0; e < n_elems; e++) {
+        int64_t t = types[e];
+        if (t < 0 || t >= NPB_N_TYPES || nfael[t] < 0) {
+            npb_set_error("element %lld has type %lld, which is not a cell type of a %d-D mesh", (long long)e, (long long)t, dim);
+            return NPB_ERR_ARG;
+        }
+        present[t] = true;
+    }
+    for (int t = 0; t < NPB_N_TYPES; t++) {
+        if (present[t]) {
             if (npoel[t] > mxp) mxp = (int)npoel[t];
             if (nfael[t] > mxf) mxf = (int)nfael[t];
         }

@@ -124,7 +124,9 @@ k_ls(const int32_t *__restrict__ esup_ptr, const int32_t *__restrict__ esup, con
         rowcnt[p] = cnt;
         return;
     }
-    if (flat) Izz = -1.0;  // ls.pyx:105-106
+    // ls.pyx:105-106 tests the same condition again, but Izz is 1.0 by now whenever it held, so the
+    // reference never sets Izz = -1.0; restated literally
+    if (Iz == 0.0 && Izz == 0.0 && Ixz == 0.0 && Iyz == 0.0) Izz = -1.0;
     double lx = __ddiv_rn(A2(A2(M2(Ix, S2(M2(Iyz, Iyz), M2(Iyy, Izz))), M2(Iy, S2(M2(Ixy, Izz), M2(Iyz, Ixz)))),
                              M2(Iz, S2(M2(Iyy, Ixz), M2(Ixy, Iyz)))), D);
     double ly = __ddiv_rn(A2(A2(M2(Ix, S2(M2(Ixy, Izz), M2(Iyz, Ixz))), M2(Iy, S2(M2(Ixz, Ixz), M2(Ixx, Izz)))),

@@ -223,7 +223,9 @@ __global__ void __launch_bounds__(TILE_T, 5) k_ls_tile(TileArgs a)
                 s_lam[4 * tid + 3] = total;
                 s_mode[tid] = 1;
             } else {
-                if (flat) Izz = -1.0;
+                // ls.pyx:105-106 repeats the test, but Izz is already 1.0 whenever it held: the reference
+                // never reaches Izz = -1.0; restated literally
+                if (Iz == 0.0 && Izz == 0.0 && Ixz == 0.0 && Iyz == 0.0) Izz = -1.0;
                 double lx = __ddiv_rn(A2(A2(M2(Ix, S2(M2(Iyz, Iyz), M2(Iyy, Izz))), M2(Iy, S2(M2(Ixy, Izz), M2(Iyz, Ixz)))),
                                          M2(Iz, S2(M2(Iyy, Ixz), M2(Ixy, Iyz)))), D);
                 double ly = __ddiv_rn(A2(A2(M2(Ix, S2(M2(Ixy, Izz), M2(Iyz, Ixz))), M2(Iy, S2(M2(Ixz, Ixz), M2(Ixx, Izz)))),
