@@ -1,3 +1,3 @@
-python tools/run_once.py tet 120 idw,ls > gpurun_out/plain.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"k_idw_tile|k_ls_tile" -c 2 -o gpurun_out/prof_tiles python tools/run_once.py tet 120 idw,ls > gpurun_out/ncu.log 2>&1
-tail -3 gpurun_out/plain.log; tail -3 gpurun_out/ncu.log
+python tools/run_once.py tet 40 gls 2 > gpurun_out/plain.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:k_gls_mf -s 2 -c 1 -o gpurun_out/prof_gls_mf_g python tools/run_once.py tet 40 gls > gpurun_out/ncu.log 2>&1
+tail -1 gpurun_out/plain.log | cut -c1-200

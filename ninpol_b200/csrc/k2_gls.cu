@@ -37,25 +37,25 @@ typedef unsigned long long u64;
 #define MF_SCAP 64           // max row groups merged into one front
 
 struct MfClass {
-    int acap;   // arena capacity (doubles); the global R slab of a CTA has the same capacity
+    int fcap;   // front buffer in shared memory (doubles)
     int ecap;   // max elements around the node
-    int fcap;   // max faces around the node
+    int fcap_f; // max faces around the node
+    int acap;   // capacity (doubles) of the CTA's global row-group arena; the R slab has the same size
 };
-#define MF_CLASS_TABLE {{0, 0, 0}, {1152, 8, 14}, {1792, 12, 22}, {2560, 16, 30}, {3840, 24, 40}, {5632, 32, 56}, \
-                        {8704, 48, 80}, {12800, 64, 112}, {0, 0, 0}}
+#define MF_CLASS_TABLE {{0, 0, 0, 0}, {512, 8, 14, 3072}, {1024, 12, 22, 6144}, {1280, 16, 30, 8192}, {1792, 24, 40, 11264}, \
+                        {2560, 32, 56, 16384}, {4096, 48, 80, 28672}, {6144, 64, 112, 40960}, {0, 0, 0, 0}}
 __constant__ MfClass c_mf[MF_NCLASS] = MF_CLASS_TABLE;
 static const MfClass h_mf[MF_NCLASS] = MF_CLASS_TABLE;
 
-__host__ __device__ __forceinline__ int mf_ngcap(const MfClass &k) { return ((2 * k.ecap + k.fcap + 7) / 8) * 8; }
-__host__ __device__ __forceinline__ int mf_mcap(const MfClass &k) { int m = k.ecap + 4 * k.fcap; return m < 96 ? m : 96; }
+__host__ __device__ __forceinline__ int mf_ngcap(const MfClass &k) { return ((2 * k.ecap + k.fcap_f + 7) / 8) * 8; }
+__host__ __device__ __forceinline__ int mf_mcap(const MfClass &k) { int m = k.ecap + 4 * k.fcap_f; return m < 96 ? m : 96; }
 __host__ __device__ __forceinline__ size_t mf_smem_bytes(const MfClass &k)
 {
-    size_t d = (size_t)k.acap + 4 * (size_t)mf_mcap(k) + 6 * (size_t)k.ecap;  // arena, vbuf[.][4], gvec, dvec
+    size_t d = (size_t)k.fcap + 4 * (size_t)mf_mcap(k) + 6 * (size_t)k.ecap;  // front, vbuf[.][4], gvec, dvec
     size_t b = d * 8 + (size_t)mf_ngcap(k) * (8 + 4 + 2 + 1) + (size_t)k.ecap * (8 + 4 + 4);   // group table, R table
     b += (size_t)k.ecap * 4 + MF_SCAP * 4 + 64;                             // es, S list, colblk
     return (b + 15) & ~(size_t)15;
 }
-__host__ __device__ __forceinline__ int mf_arena_need(int E, int m) { (void)E; return 22 * m + 64; }
 
 // per node: Dirichlet / Q8 nodes are finished here (zero row); the others get a size class
 __global__ void k_gls_classify(GlsArgs a, i64 lo, i64 hi, uint8_t *__restrict__ cls, int force_dense)
@@ -80,11 +80,9 @@ __global__ void k_gls_classify(GlsArgs a, i64 lo, i64 hi, uint8_t *__restrict__ 
         cls[p] = 0;
         return;
     }
-    int m = E + 3 * (F - nb) + (neu ? nb : 0);
-    int need = mf_arena_need(E, m);
     int k = MF_NCLASS - 1;
     for (int q = 1; q < MF_NCLASS - 1 && !force_dense; q++)
-        if (E <= c_mf[q].ecap && F <= c_mf[q].fcap && need <= c_mf[q].acap) {
+        if (E <= c_mf[q].ecap && F <= c_mf[q].fcap_f) {
             k = q;
             break;
         }
@@ -97,6 +95,14 @@ __device__ __forceinline__ u64 warp_or64(u64 v)
     unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
     return ((u64)hi << 32) | lo;
 }
+// 8-byte asynchronous global -> shared copy (LDGSTS): no register staging, no stall until the wait
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gmem_src)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ int nth_set_bit(u64 m, int n)  // index of the n-th (0-based) set bit
 {
     for (int q = 0; q < n; q++) m &= m - 1;
@@ -104,7 +110,9 @@ __device__ __forceinline__ int nth_set_bit(u64 m, int n)  // index of the n-th (
 }
 
 struct MfWs {
-    double *arena, *vbuf, *gvec, *dvec;
+    double *arena;   // global: row groups (original rows, contribution blocks), append-only
+    double *front;   // shared: the dense front being factored
+    double *vbuf, *gvec, *dvec;
     u64 *g_mask, *r_mask;
     int *g_off, *r_off, *r_meta;   // r_meta = piv | npiv << 8 | c << 16
     unsigned short *g_nr;
@@ -114,12 +122,13 @@ struct MfWs {
     unsigned char *colblk;  // block id of every 3-column slot of the current front
 };
 
-__device__ __forceinline__ MfWs mf_carve(unsigned char *base, const MfClass &k)
+__device__ __forceinline__ MfWs mf_carve(unsigned char *base, const MfClass &k, double *garena)
 {
     MfWs w;
     int ng = mf_ngcap(k);
-    w.arena = (double *)base;
-    w.vbuf = w.arena + k.acap;                  // [mcap][4]: the three Householder vectors of a front
+    w.arena = garena;
+    w.front = (double *)base;
+    w.vbuf = w.front + k.fcap;                  // [mcap][4]: the three Householder vectors of a front
     w.gvec = w.vbuf + 4 * mf_mcap(k);
     w.dvec = w.gvec + 3 * k.ecap;
     w.g_mask = (u64 *)(w.dvec + 3 * k.ecap);
@@ -133,43 +142,6 @@ __device__ __forceinline__ MfWs mf_carve(unsigned char *base, const MfClass &k)
     w.g_ld = (unsigned char *)(w.g_nr + ng);
     w.colblk = w.g_ld + ng;                     // [64]
     return w;
-}
-
-// Closes the holes left by consumed groups: live table entries (and their arena blocks) slide down in
-// table order, which equals arena order because entries are only ever appended at the arena top.
-__device__ void mf_compact(MfWs &w, int &ng, int &top, int lane)
-{
-    int newng = 0, newtop = 0;
-    for (int g0 = 0; g0 < ng; g0 += 32) {
-        int g = g0 + lane;
-        unsigned bal = __ballot_sync(0xffffffffu, g < ng && w.g_nr[g] > 0);
-        while (bal) {
-            int gi = g0 + __ffs(bal) - 1;
-            bal &= bal - 1;
-            u64 mk = w.g_mask[gi];
-            int src = w.g_off[gi], nr = w.g_nr[gi], ld = w.g_ld[gi];
-            int sz = nr * ld;
-            if (src != newtop) {
-                for (int i = lane; i < sz; i += 32) {
-                    double v = w.arena[src + i];
-                    __syncwarp(__activemask());
-                    w.arena[newtop + i] = v;
-                }
-            }
-            __syncwarp();
-            if (lane == 0) {
-                w.g_mask[newng] = mk;
-                w.g_off[newng] = newtop;
-                w.g_nr[newng] = (unsigned short)nr;
-                w.g_ld[newng] = (unsigned char)ld;
-            }
-            newtop += sz;
-            newng++;
-        }
-    }
-    __syncwarp();
-    ng = newng;
-    top = newtop;
 }
 
 #define MF_RPL 3   // front rows per lane in the panel factorisation: fronts of up to 96 rows
@@ -187,11 +159,11 @@ __device__ __forceinline__ void hh_scalars(double sigma, double x0, double &alph
 }
 
 // returns 0 on success, 1 when the star does not fit this class (caller reroutes it to the dense kernel)
-__device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfClass &kc, double *rslab)
+__device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfClass &kc, double *rslab, double *garena)
 {
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
-    MfWs w = mf_carve(smem, kc);
+    MfWs w = mf_carve(smem, kc, garena);
     const int eb = a.esup_ptr[p], E = a.esup_ptr[p + 1] - eb;
     const int fb = a.fsup_ptr[p], F = a.fsup_ptr[p + 1] - fb;
     const bool neu = a.nflag[p] != 0;
@@ -320,52 +292,48 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
         unsigned key = __reduce_min_sync(FULL, keyA < keyB ? keyA : keyB);
         const int piv = (int)(key & 0xffu);
         const u64 pbit = 1ull << piv;
-        // (b) row groups containing the pivot block; (c) room for the front at the arena top
-        int nS, rho, c, need;
-        u64 U, Up;
-        for (int attempt = 0;; attempt++) {
-            nS = 0; rho = 0; U = 0;
-            for (int g0 = 0; g0 < ng; g0 += 32) {
-                int g = g0 + lane;
-                bool in = false;
-                int nr = 0;
-                u64 mk = 0;
-                if (g < ng) {
-                    nr = w.g_nr[g];
-                    mk = w.g_mask[g];
-                    in = nr > 0 && (mk & pbit);
-                }
-                unsigned bal = __ballot_sync(FULL, in);
-                if (bal == 0) continue;
-                int v = in ? nr : 0;   // exclusive prefix of the row counts over the selected lanes
-                int incl = v;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    int t = __shfl_up_sync(FULL, incl, o);
-                    if (lane >= o) incl += t;
-                }
-                int pos = nS + __popc(bal & ((1u << lane) - 1u));
-                if (in && pos < MF_SCAP) w.s_list[pos] = g | ((rho + incl - v) << 16);
-                nS += __popc(bal);
-                rho += __shfl_sync(FULL, incl, 31);
-                U |= warp_or64(in ? mk : 0ull);
+        // (b) row groups containing the pivot block
+        int nS = 0, rho = 0;
+        u64 U = 0;
+        for (int g0 = 0; g0 < ng; g0 += 32) {
+            int g = g0 + lane;
+            bool in = false;
+            int nr = 0;
+            u64 mk = 0;
+            if (g < ng) {
+                nr = w.g_nr[g];
+                mk = w.g_mask[g];
+                in = nr > 0 && (mk & pbit);
             }
-            if (nS > MF_SCAP || rho > 32 * MF_RPL || rho > mf_mcap(kc)) return 1;
-            Up = U & ~pbit;
-            c = 3 * __popcll(U) + 1;
-            need = rho * c;
-            if (top + need <= kc.acap) break;
-            if (attempt > 0) return 1;
-            __syncwarp();
-            mf_compact(w, ng, top, lane);   // renumbers the table: select again
+            unsigned bal = __ballot_sync(FULL, in);
+            if (bal == 0) continue;
+            int v = in ? nr : 0;   // exclusive prefix of the row counts over the selected lanes
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += t;
+            }
+            int pos = nS + __popc(bal & ((1u << lane) - 1u));
+            if (in && pos < MF_SCAP) w.s_list[pos] = g | ((rho + incl - v) << 16);
+            nS += __popc(bal);
+            rho += __shfl_sync(FULL, incl, 31);
+            U |= warp_or64(in ? mk : 0ull);
         }
-        if (ng + 1 > ngcap || rtop + 3 * c > kc.acap) return 1;
+        const u64 Up = U & ~pbit;
+        const int c = 3 * __popcll(U) + 1;
+        const int npiv = rho < 3 ? rho : 3;
+        const int left = rho - npiv;
+        const bool keep = left > 0 && Up != 0;
+        // (c) capacity checks: front buffer (shared), group arena and R slab (global), tables
+        if (nS > MF_SCAP || rho > 32 * MF_RPL || rho > mf_mcap(kc) || rho * c > kc.fcap) return 1;
+        if (ng + 1 > ngcap || rtop + 3 * c > kc.acap || (keep && top + left * (c - 3) > kc.acap)) return 1;
         // block id of every column slot: slot 0 = pivot, then the other blocks ascending
         if ((Up >> lane) & 1ull) w.colblk[1 + __popcll(Up & ((1ull << lane) - 1ull))] = (unsigned char)lane;
         if ((Up >> (lane + 32)) & 1ull) w.colblk[1 + __popcll(Up & ((1ull << (lane + 32)) - 1ull))] = (unsigned char)(lane + 32);
         if (lane == 0) w.colblk[0] = (unsigned char)piv;
         __syncwarp();
-        double *Fm = w.arena + top;
+        double *Fm = w.front;
         // (d) assemble: lanes over front columns [pivot block | other blocks ascending | rhs]
         for (int j0 = 0; j0 < c; j0 += 32) {
             int j = j0 + lane;
@@ -383,13 +351,21 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
                 int sc = is_rhs ? 3 * __popcll(mk) : 3 * __popcll(mk & below) + comp;
                 const double *src = w.arena + w.g_off[g] + sc;
                 double *dst = Fm + (packed >> 16) * c + j;
-                for (int r = 0; r < nr; r++) {
-                    *dst = has ? *src : 0.0;
-                    src += ld;
-                    dst += c;
+                if (has) {
+                    for (int r = 0; r < nr; r++) {
+                        cp_async8(dst, src);   // row groups live in global memory: all copies of a front in flight at once
+                        src += ld;
+                        dst += c;
+                    }
+                } else {
+                    for (int r = 0; r < nr; r++) {
+                        *dst = 0.0;
+                        dst += c;
+                    }
                 }
             }
         }
+        cp_async_wait_all();
         __syncwarp();
         for (int t = lane; t < nS; t += 32) w.g_nr[w.s_list[t] & 0xffff] = 0;   // consumed
         // (e) panel: Householder on the three pivot columns, lanes over rows, entries in registers
@@ -505,26 +481,39 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
             }
         }
         __syncwarp();
-        // (g) the pivot rows go to the R slab (global, L2-resident); the remaining rows stay as a new group
-        const int npiv = rho < 3 ? rho : 3;
-        const int left = rho - npiv;
-        const bool keep = left > 0 && Up != 0;
+        // (g) the pivot rows go to the R slab, the remaining rows (columns of the other blocks + rhs) are
+        //     appended to the group arena as one new contribution block; both live in global memory
         for (int j = lane; j < npiv * c; j += 32) rslab[rtop + j] = Fm[j];
+        if (keep) {
+            const int cw = c - 3;
+            for (int j0 = 0; j0 < cw; j0 += 32) {
+                int j = j0 + lane;
+                if (j < cw) {
+                    const double *src = Fm + npiv * c + 3 + j;
+                    double *dst = w.arena + top + j;
+                    for (int r = 0; r < left; r++) {
+                        *dst = *src;
+                        src += c;
+                        dst += cw;
+                    }
+                }
+            }
+        }
         if (lane == 0) {
             w.r_mask[nR] = U;
             w.r_off[nR] = rtop;
             w.r_meta[nR] = piv | (npiv << 8) | (c << 16);
             if (keep) {
                 w.g_mask[ng] = Up;
-                w.g_off[ng] = top + npiv * c + 3;
+                w.g_off[ng] = top;
                 w.g_nr[ng] = (unsigned short)left;
-                w.g_ld[ng] = (unsigned char)c;
+                w.g_ld[ng] = (unsigned char)(c - 3);
             }
         }
         nR++;
         rtop += npiv * c;
         if (keep) {
-            top += need;
+            top += left * (c - 3);
             ng++;
         }
         // (h) adjacency update: the neighbours of the pivot become a clique
@@ -536,14 +525,19 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
 
     // ---- back substitution through the R rows, newest first (slab copied back into the free arena) ----
     __syncwarp();
-    for (int i = lane; i < rtop; i += 32) w.arena[i] = rslab[i];
+    const bool r_in_smem = rtop <= kc.fcap;
+    if (r_in_smem) {
+        for (int i = lane; i < rtop; i += 32) cp_async8(w.front + i, rslab + i);
+        cp_async_wait_all();
+    }
+    const double *Rbase = r_in_smem ? w.front : rslab;
     for (int i = lane; i < 3 * E; i += 32) w.gvec[i] = 0.0;
     __syncwarp();
     for (int g = nR - 1; g >= 0; g--) {
         const int meta = w.r_meta[g];
         const int piv = meta & 0xff, npiv = (meta >> 8) & 0xff, c = meta >> 16;
         const u64 Up = w.r_mask[g] & ~(1ull << piv);
-        const double *R = w.arena + w.r_off[g];
+        const double *R = Rbase + w.r_off[g];
         double p0 = 0.0, p1 = 0.0, p2 = 0.0;
         for (int j0 = 3; j0 < c - 1; j0 += 32) {
             int j = j0 + lane;
@@ -609,20 +603,24 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
 
 // persistent: one warp per CTA; nodes handed out through an atomic counter; stars that do not fit are
 // appended to the overflow list for the dense kernel
-__global__ void __launch_bounds__(32)
+#ifndef MF_MINBLOCKS
+#define MF_MINBLOCKS 12
+#endif
+__global__ void __launch_bounds__(32, MF_MINBLOCKS)
 k_gls_mf(GlsArgs a, const int32_t *__restrict__ list, int count, int *__restrict__ counter, int klass,
-         int32_t *__restrict__ overflow, int *__restrict__ n_overflow, double *__restrict__ rslabs)
+         int32_t *__restrict__ overflow, int *__restrict__ n_overflow, double *__restrict__ slabs)
 {
     extern __shared__ __align__(16) unsigned char smem_mf[];
     const MfClass kc = c_mf[klass];
-    double *rslab = rslabs + (size_t)blockIdx.x * kc.acap;
+    double *rslab = slabs + (size_t)blockIdx.x * kc.acap * 2;   // per CTA: R slab, then the group arena
+    double *garena = rslab + kc.acap;
     while (true) {
         int i = 0;
         if (threadIdx.x == 0) i = atomicAdd(counter, 1);
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= count) break;
         int p = list[i];
-        int rc = mf_node(a, p, smem_mf, kc, rslab);
+        int rc = mf_node(a, p, smem_mf, kc, rslab, garena);
         __syncwarp();
         if (rc != 0 && threadIdx.x == 0) overflow[atomicAdd(n_overflow, 1)] = p;
     }
@@ -663,10 +661,12 @@ int npb_k2_gls(npb_ctx *c, i64 lo, i64 hi)
         int smem = (int)mf_smem_bytes(h_mf[k]);
         NPB_CUDA(cudaFuncSetAttribute(k_gls_mf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int per_sm = (int)((227 * 1024) / (smem + 1024));
+        const char *cap = getenv("NPB_GLS_CTAS_PER_SM");
+        if (cap && atoi(cap) > 0 && per_sm > atoi(cap)) per_sm = atoi(cap);
         if (per_sm > 32) per_sm = 32;
         int grid = c->sm_count * per_sm;
         if (grid > count) grid = count;
-        NPB_TRY(npb_ensure(&c->gls_ws, &c->gls_ws_cap, sizeof(double) * (size_t)grid * h_mf[k].acap));
+        NPB_TRY(npb_ensure(&c->gls_ws, &c->gls_ws_cap, sizeof(double) * (size_t)grid * h_mf[k].acap * 2));
         k_gls_mf<<<grid, 32, smem, s>>>(a, list, count, counter, k, overflow, n_overflow, (double *)c->gls_ws);
         NPB_LAUNCH(c);
         NPB_CUDA(cudaGetLastError());
