@@ -23,11 +23,16 @@
 // for a dense one-RHS QR (1.94 MFLOP in the reference).  Back substitution through the stored R rows
 // gives g, then r_i = 1 - d_i . g_i on the element rows.
 //
-// Mapping: one warp per node; fronts, row groups and R live in a per-warp shared-memory arena with
-// in-place compaction; lanes run over front columns, loops over front rows.  Nodes are bucketed by
-// star size so small stars get many resident warps; stars that do not fit (E > 64, arena overflow) go
-// to the dense global-memory kernel of k2_gls_dense.cu.  FP64-FMA / shared-memory bound, not HBM bound
-// (SURVEY.md Q13).
+// Mapping: one warp per node (one-warp CTAs, persistent, atomic work counter).  The dense front being
+// factored lives in shared memory (lanes over front columns, loops over front rows; the 3-column panel is
+// factored with lanes over rows in registers + shuffles); the row groups — original rows and the
+// contribution blocks left by earlier fronts — and the finished rows of R live in an append-only,
+// L2-resident global slab per CTA and are fetched into the front with cp.async (LDGSTS), so shared
+// memory holds only the hot data and ~10-27 nodes are resident per SM instead of 6.  Fronts taller than
+// the shared buffer are processed in row chunks (the 3 pivot rows of a chunk are carried into the next).
+// Nodes are bucketed into 7 size classes by star size; stars that do not fit (E > 64, a capacity
+// overflow detected at run time) go to the dense global-memory kernel of k2_gls_dense.cu.  The kernel is
+// latency / issue bound on this bookkeeping, not FP64 or HBM bound (profiles/).
 #include <stdlib.h>
 #include "gls_common.cuh"
 
@@ -42,8 +47,8 @@ struct MfClass {
     int fcap_f; // max faces around the node
     int acap;   // capacity (doubles) of the CTA's global row-group arena; the R slab has the same size
 };
-#define MF_CLASS_TABLE {{0, 0, 0, 0}, {512, 8, 14, 3072}, {1024, 12, 22, 6144}, {1280, 16, 30, 8192}, {1792, 24, 40, 11264}, \
-                        {2560, 32, 56, 16384}, {4096, 48, 80, 28672}, {6144, 64, 112, 40960}, {0, 0, 0, 0}}
+#define MF_CLASS_TABLE {{0, 0, 0, 0}, {384, 8, 14, 3072}, {640, 12, 22, 6144}, {768, 16, 30, 8192}, {1408, 24, 40, 12288}, \
+                        {1536, 32, 56, 18432}, {2560, 48, 80, 32768}, {4096, 64, 112, 49152}, {0, 0, 0, 0}}
 __constant__ MfClass c_mf[MF_NCLASS] = MF_CLASS_TABLE;
 static const MfClass h_mf[MF_NCLASS] = MF_CLASS_TABLE;
 
@@ -322,200 +327,217 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
         }
         const u64 Up = U & ~pbit;
         const int c = 3 * __popcll(U) + 1;
-        const int npiv = rho < 3 ? rho : 3;
-        const int left = rho - npiv;
-        const bool keep = left > 0 && Up != 0;
-        // (c) capacity checks: front buffer (shared), group arena and R slab (global), tables
-        if (nS > MF_SCAP || rho > 32 * MF_RPL || rho > mf_mcap(kc) || rho * c > kc.fcap) return 1;
-        if (ng + 1 > ngcap || rtop + 3 * c > kc.acap || (keep && top + left * (c - 3) > kc.acap)) return 1;
+        // (c) capacity checks: group table, R slab; the front is processed in chunks of at most `rcap` rows
+        const int rcap = min(32 * MF_RPL, min(mf_mcap(kc), kc.fcap / c));
+        if (nS > MF_SCAP || rcap < 8 || rtop + 3 * c > kc.acap) return 1;
         // block id of every column slot: slot 0 = pivot, then the other blocks ascending
         if ((Up >> lane) & 1ull) w.colblk[1 + __popcll(Up & ((1ull << lane) - 1ull))] = (unsigned char)lane;
         if ((Up >> (lane + 32)) & 1ull) w.colblk[1 + __popcll(Up & ((1ull << (lane + 32)) - 1ull))] = (unsigned char)(lane + 32);
         if (lane == 0) w.colblk[0] = (unsigned char)piv;
         __syncwarp();
         double *Fm = w.front;
-        // (d) assemble: lanes over front columns [pivot block | other blocks ascending | rhs]
-        for (int j0 = 0; j0 < c; j0 += 32) {
-            int j = j0 + lane;
-            if (j >= c) continue;
-            const bool is_rhs = (j == c - 1);
-            const int blk = is_rhs ? 0 : w.colblk[j / 3];
-            const int comp = j % 3;
-            const u64 below = (1ull << blk) - 1ull;
-            for (int t = 0; t < nS; t++) {
-                int packed = w.s_list[t];
-                int g = packed & 0xffff;
-                u64 mk = w.g_mask[g];
-                int nr = w.g_nr[g], ld = w.g_ld[g];
-                bool has = is_rhs || ((mk >> blk) & 1ull);
-                int sc = is_rhs ? 3 * __popcll(mk) : 3 * __popcll(mk & below) + comp;
-                const double *src = w.arena + w.g_off[g] + sc;
-                double *dst = Fm + (packed >> 16) * c + j;
-                if (has) {
-                    for (int r = 0; r < nr; r++) {
-                        cp_async8(dst, src);   // row groups live in global memory: all copies of a front in flight at once
-                        src += ld;
-                        dst += c;
+        const int ng0 = ng;         // groups appended below are not candidates of this elimination
+        int t_next = 0, r_done = 0; // next group of the S list / rows of it already taken
+        int carry = 0;              // pivot rows of the previous chunk, kept in front rows [0, carry)
+        int npiv = 0;
+        (void)rho;
+        for (bool last = false; !last;) {
+            // (d) assemble one chunk: lanes over front columns [pivot block | other blocks ascending | rhs]
+            int rho_c = carry;
+            while (t_next < nS && rho_c < rcap) {
+                const int g = w.s_list[t_next] & 0xffff;
+                const u64 mk = w.g_mask[g];
+                const int nr = w.g_nr[g], ld = w.g_ld[g];
+                const int take = min(nr - r_done, rcap - rho_c);
+                const double *gsrc = w.arena + w.g_off[g] + r_done * ld;
+                for (int j0 = 0; j0 < c; j0 += 32) {
+                    int j = j0 + lane;
+                    if (j >= c) continue;
+                    const bool is_rhs = (j == c - 1);
+                    const int blk = is_rhs ? 0 : w.colblk[j / 3];
+                    const bool has = is_rhs || ((mk >> blk) & 1ull);
+                    const int sc = is_rhs ? 3 * __popcll(mk) : 3 * __popcll(mk & ((1ull << blk) - 1ull)) + j % 3;
+                    const double *src = gsrc + sc;
+                    double *dst = Fm + rho_c * c + j;
+                    if (has) {
+                        for (int r = 0; r < take; r++) {
+                            cp_async8(dst, src);   // row groups live in global memory: all copies of a chunk in flight at once
+                            src += ld;
+                            dst += c;
+                        }
+                    } else {
+                        for (int r = 0; r < take; r++) {
+                            *dst = 0.0;
+                            dst += c;
+                        }
                     }
-                } else {
-                    for (int r = 0; r < nr; r++) {
-                        *dst = 0.0;
-                        dst += c;
-                    }
+                }
+                rho_c += take;
+                r_done += take;
+                if (r_done == nr) {
+                    t_next++;
+                    r_done = 0;
                 }
             }
-        }
-        cp_async_wait_all();
-        __syncwarp();
-        for (int t = lane; t < nS; t += 32) w.g_nr[w.s_list[t] & 0xffff] = 0;   // consumed
-        // (e) panel: Householder on the three pivot columns, lanes over rows, entries in registers
-        double a0[MF_RPL], a1[MF_RPL], a2[MF_RPL];
+            last = (t_next >= nS);
+            cp_async_wait_all();
+            __syncwarp();
+            // (e) panel: Householder on the three pivot columns, lanes over rows, entries in registers
+            double a0[MF_RPL], a1[MF_RPL], a2[MF_RPL];
 #pragma unroll
-        for (int q = 0; q < MF_RPL; q++) {
-            int r = lane + 32 * q;
-            bool ok = r < rho;
-            a0[q] = ok ? Fm[r * c + 0] : 0.0;
-            a1[q] = ok ? Fm[r * c + 1] : 0.0;
-            a2[q] = ok ? Fm[r * c + 2] : 0.0;
-        }
-        double alpha0, beta0, alpha1, beta1, alpha2, beta2, d10, d20, d21;
-        {
-            double sg = 0.0;
-#pragma unroll
-            for (int q = 0; q < MF_RPL; q++) sg += a0[q] * a0[q];
-            sg = warp_sum(sg);
-            double x00 = __shfl_sync(FULL, a0[0], 0);
-            hh_scalars(sg, x00, alpha0, beta0);
-            if (lane == 0) a0[0] = x00 - alpha0;                  // a0 now holds v0
-            double t1 = 0.0, t2 = 0.0;
-#pragma unroll
-            for (int q = 0; q < MF_RPL; q++) { t1 += a0[q] * a1[q]; t2 += a0[q] * a2[q]; }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { t1 += __shfl_xor_sync(FULL, t1, o); t2 += __shfl_xor_sync(FULL, t2, o); }
-            t1 *= beta0; t2 *= beta0;
-#pragma unroll
-            for (int q = 0; q < MF_RPL; q++) { a1[q] -= t1 * a0[q]; a2[q] -= t2 * a0[q]; }
-        }
-        double r01 = __shfl_sync(FULL, a1[0], 0), r02 = __shfl_sync(FULL, a2[0], 0);
-        {
-            if (lane == 0) a1[0] = 0.0;                           // rows above the pivot do not take part
-            double sg = 0.0;
-#pragma unroll
-            for (int q = 0; q < MF_RPL; q++) sg += a1[q] * a1[q];
-            sg = warp_sum(sg);
-            double x11 = __shfl_sync(FULL, a1[0], 1);
-            hh_scalars(sg, x11, alpha1, beta1);
-            if (lane == 1) a1[0] = x11 - alpha1;                  // a1 now holds v1
-            if (lane == 0) a2[0] = 0.0;
-            double t2 = 0.0;
-#pragma unroll
-            for (int q = 0; q < MF_RPL; q++) t2 += a1[q] * a2[q];
-            t2 = warp_sum(t2) * beta1;
-#pragma unroll
-            for (int q = 0; q < MF_RPL; q++) a2[q] -= t2 * a1[q];
-        }
-        double r12 = __shfl_sync(FULL, a2[0], 1);
-        {
-            if (lane == 1) a2[0] = 0.0;
-            double sg = 0.0;
-#pragma unroll
-            for (int q = 0; q < MF_RPL; q++) sg += a2[q] * a2[q];
-            sg = warp_sum(sg);
-            double x22 = __shfl_sync(FULL, a2[0], 2);
-            hh_scalars(sg, x22, alpha2, beta2);
-            if (lane == 2) a2[0] = x22 - alpha2;                  // a2 now holds v2
-            d10 = 0.0; d20 = 0.0; d21 = 0.0;
-#pragma unroll
-            for (int q = 0; q < MF_RPL; q++) { d10 += a1[q] * a0[q]; d20 += a2[q] * a0[q]; d21 += a2[q] * a1[q]; }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                d10 += __shfl_xor_sync(FULL, d10, o);
-                d20 += __shfl_xor_sync(FULL, d20, o);
-                d21 += __shfl_xor_sync(FULL, d21, o);
+            for (int q = 0; q < MF_RPL; q++) {
+                int r = lane + 32 * q;
+                bool ok = r < rho_c;
+                a0[q] = ok ? Fm[r * c + 0] : 0.0;
+                a1[q] = ok ? Fm[r * c + 1] : 0.0;
+                a2[q] = ok ? Fm[r * c + 2] : 0.0;
             }
-        }
-        // v vectors to shared memory as [row][4]; the pivot rows' panel entries of R
-#pragma unroll
-        for (int q = 0; q < MF_RPL; q++) {
-            int r = lane + 32 * q;
-            if (r < rho) {
-                double2 *vp = reinterpret_cast<double2 *>(w.vbuf + 4 * r);
-                vp[0] = make_double2(a0[q], a1[q]);
-                vp[1] = make_double2(a2[q], 0.0);
-            }
-        }
-        if (lane == 0) {
-            Fm[0] = alpha0; Fm[1] = r01; Fm[2] = r02;
-            if (rho > 1) { Fm[c + 1] = alpha1; Fm[c + 2] = r12; }
-            if (rho > 2) Fm[2 * c + 2] = alpha2;
-        }
-        __syncwarp();
-        // (f) apply the three reflections to the other columns: two passes over the rows
-        for (int j0 = 3; j0 < c; j0 += 32) {
-            int j = j0 + lane;
-            if (j >= c) continue;
-            double w0 = 0.0, w1 = 0.0, w2 = 0.0;
+            double alpha0, beta0, alpha1, beta1, alpha2, beta2, d10, d20, d21;
             {
-                const double *fp = Fm + j;
-                const double2 *vp = reinterpret_cast<const double2 *>(w.vbuf);
-#pragma unroll 4
-                for (int r = 0; r < rho; r++) {
-                    double f = *fp;
-                    double2 va = vp[0], vb = vp[1];
-                    w0 += va.x * f; w1 += va.y * f; w2 += vb.x * f;
-                    fp += c; vp += 2;
-                }
+                double sg = 0.0;
+#pragma unroll
+                for (int q = 0; q < MF_RPL; q++) sg += a0[q] * a0[q];
+                sg = warp_sum(sg);
+                double x00 = __shfl_sync(FULL, a0[0], 0);
+                hh_scalars(sg, x00, alpha0, beta0);
+                if (lane == 0) a0[0] = x00 - alpha0;                  // a0 now holds v0
+                double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+                for (int q = 0; q < MF_RPL; q++) { t1 += a0[q] * a1[q]; t2 += a0[q] * a2[q]; }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { t1 += __shfl_xor_sync(FULL, t1, o); t2 += __shfl_xor_sync(FULL, t2, o); }
+                t1 *= beta0; t2 *= beta0;
+#pragma unroll
+                for (int q = 0; q < MF_RPL; q++) { a1[q] -= t1 * a0[q]; a2[q] -= t2 * a0[q]; }
             }
-            double s0 = beta0 * w0;
-            double s1 = beta1 * (w1 - d10 * s0);
-            double s2 = beta2 * (w2 - d20 * s0 - d21 * s1);
+            double r01 = __shfl_sync(FULL, a1[0], 0), r02 = __shfl_sync(FULL, a2[0], 0);
             {
-                double *fp = Fm + j;
-                const double2 *vp = reinterpret_cast<const double2 *>(w.vbuf);
-#pragma unroll 4
-                for (int r = 0; r < rho; r++) {
-                    double2 va = vp[0], vb = vp[1];
-                    *fp = *fp - (va.x * s0 + va.y * s1 + vb.x * s2);
-                    fp += c; vp += 2;
+                if (lane == 0) a1[0] = 0.0;                           // rows above the pivot do not take part
+                double sg = 0.0;
+#pragma unroll
+                for (int q = 0; q < MF_RPL; q++) sg += a1[q] * a1[q];
+                sg = warp_sum(sg);
+                double x11 = __shfl_sync(FULL, a1[0], 1);
+                hh_scalars(sg, x11, alpha1, beta1);
+                if (lane == 1) a1[0] = x11 - alpha1;                  // a1 now holds v1
+                if (lane == 0) a2[0] = 0.0;
+                double t2 = 0.0;
+#pragma unroll
+                for (int q = 0; q < MF_RPL; q++) t2 += a1[q] * a2[q];
+                t2 = warp_sum(t2) * beta1;
+#pragma unroll
+                for (int q = 0; q < MF_RPL; q++) a2[q] -= t2 * a1[q];
+            }
+            double r12 = __shfl_sync(FULL, a2[0], 1);
+            {
+                if (lane == 1) a2[0] = 0.0;
+                double sg = 0.0;
+#pragma unroll
+                for (int q = 0; q < MF_RPL; q++) sg += a2[q] * a2[q];
+                sg = warp_sum(sg);
+                double x22 = __shfl_sync(FULL, a2[0], 2);
+                hh_scalars(sg, x22, alpha2, beta2);
+                if (lane == 2) a2[0] = x22 - alpha2;                  // a2 now holds v2
+                d10 = 0.0; d20 = 0.0; d21 = 0.0;
+#pragma unroll
+                for (int q = 0; q < MF_RPL; q++) { d10 += a1[q] * a0[q]; d20 += a2[q] * a0[q]; d21 += a2[q] * a1[q]; }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    d10 += __shfl_xor_sync(FULL, d10, o);
+                    d20 += __shfl_xor_sync(FULL, d20, o);
+                    d21 += __shfl_xor_sync(FULL, d21, o);
                 }
             }
-        }
-        __syncwarp();
-        // (g) the pivot rows go to the R slab, the remaining rows (columns of the other blocks + rhs) are
-        //     appended to the group arena as one new contribution block; both live in global memory
-        for (int j = lane; j < npiv * c; j += 32) rslab[rtop + j] = Fm[j];
-        if (keep) {
-            const int cw = c - 3;
-            for (int j0 = 0; j0 < cw; j0 += 32) {
+            // v vectors to shared memory as [row][4]; the pivot rows' panel entries of R
+#pragma unroll
+            for (int q = 0; q < MF_RPL; q++) {
+                int r = lane + 32 * q;
+                if (r < rho_c) {
+                    double2 *vp = reinterpret_cast<double2 *>(w.vbuf + 4 * r);
+                    vp[0] = make_double2(a0[q], a1[q]);
+                    vp[1] = make_double2(a2[q], 0.0);
+                }
+            }
+            if (lane == 0) {
+                Fm[0] = alpha0; Fm[1] = r01; Fm[2] = r02;
+                if (rho_c > 1) { Fm[c] = 0.0; Fm[c + 1] = alpha1; Fm[c + 2] = r12; }
+                if (rho_c > 2) { Fm[2 * c] = 0.0; Fm[2 * c + 1] = 0.0; Fm[2 * c + 2] = alpha2; }
+            }
+            __syncwarp();
+            // (f) apply the three reflections to the other columns: two passes over the rows
+            for (int j0 = 3; j0 < c; j0 += 32) {
                 int j = j0 + lane;
-                if (j < cw) {
-                    const double *src = Fm + npiv * c + 3 + j;
-                    double *dst = w.arena + top + j;
-                    for (int r = 0; r < left; r++) {
-                        *dst = *src;
-                        src += c;
-                        dst += cw;
+                if (j >= c) continue;
+                double w0 = 0.0, w1 = 0.0, w2 = 0.0;
+                {
+                    const double *fp = Fm + j;
+                    const double2 *vp = reinterpret_cast<const double2 *>(w.vbuf);
+#pragma unroll 4
+                    for (int r = 0; r < rho_c; r++) {
+                        double f = *fp;
+                        double2 va = vp[0], vb = vp[1];
+                        w0 += va.x * f; w1 += va.y * f; w2 += vb.x * f;
+                        fp += c; vp += 2;
+                    }
+                }
+                double s0 = beta0 * w0;
+                double s1 = beta1 * (w1 - d10 * s0);
+                double s2 = beta2 * (w2 - d20 * s0 - d21 * s1);
+                {
+                    double *fp = Fm + j;
+                    const double2 *vp = reinterpret_cast<const double2 *>(w.vbuf);
+#pragma unroll 4
+                    for (int r = 0; r < rho_c; r++) {
+                        double2 va = vp[0], vb = vp[1];
+                        *fp = *fp - (va.x * s0 + va.y * s1 + vb.x * s2);
+                        fp += c; vp += 2;
                     }
                 }
             }
+            __syncwarp();
+            // (g) rows below the pivot rows (columns of the other blocks + rhs) are appended to the group arena
+            //     as a new contribution block; the pivot rows stay in the front for the next chunk, or go to
+            //     the R slab after the last one
+            npiv = rho_c < 3 ? rho_c : 3;
+            const int left = rho_c - npiv;
+            const bool keep = left > 0 && Up != 0;
+            if (keep) {
+                const int cw = c - 3;
+                if (ng + 1 > ngcap || top + left * cw > kc.acap) return 1;
+                for (int j0 = 0; j0 < cw; j0 += 32) {
+                    int j = j0 + lane;
+                    if (j < cw) {
+                        const double *src = Fm + npiv * c + 3 + j;
+                        double *dst = w.arena + top + j;
+                        for (int r = 0; r < left; r++) {
+                            *dst = *src;
+                            src += c;
+                            dst += cw;
+                        }
+                    }
+                }
+                if (lane == 0) {
+                    w.g_mask[ng] = Up;
+                    w.g_off[ng] = top;
+                    w.g_nr[ng] = (unsigned short)left;
+                    w.g_ld[ng] = (unsigned char)cw;
+                }
+                top += left * cw;
+                ng++;
+            }
+            carry = npiv;
+            __syncwarp();
         }
+        for (int t = lane; t < nS; t += 32) w.g_nr[w.s_list[t] & 0xffff] = 0;   // consumed
+        (void)ng0;
+        for (int j = lane; j < npiv * c; j += 32) rslab[rtop + j] = Fm[j];
         if (lane == 0) {
             w.r_mask[nR] = U;
             w.r_off[nR] = rtop;
             w.r_meta[nR] = piv | (npiv << 8) | (c << 16);
-            if (keep) {
-                w.g_mask[ng] = Up;
-                w.g_off[ng] = top;
-                w.g_nr[ng] = (unsigned short)left;
-                w.g_ld[ng] = (unsigned char)(c - 3);
-            }
         }
         nR++;
         rtop += npiv * c;
-        if (keep) {
-            top += left * (c - 3);
-            ng++;
-        }
         // (h) adjacency update: the neighbours of the pivot become a clique
         if ((Up >> lane) & 1ull) adjA = (adjA | U) & ~pbit;
         if ((Up >> (lane + 32)) & 1ull) adjB = (adjB | U) & ~pbit;
@@ -603,10 +625,8 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
 
 // persistent: one warp per CTA; nodes handed out through an atomic counter; stars that do not fit are
 // appended to the overflow list for the dense kernel
-#ifndef MF_MINBLOCKS
-#define MF_MINBLOCKS 12
-#endif
-__global__ void __launch_bounds__(32, MF_MINBLOCKS)
+template <int MINBLOCKS>
+__global__ void __launch_bounds__(32, MINBLOCKS)
 k_gls_mf(GlsArgs a, const int32_t *__restrict__ list, int count, int *__restrict__ counter, int klass,
          int32_t *__restrict__ overflow, int *__restrict__ n_overflow, double *__restrict__ slabs)
 {
@@ -659,7 +679,11 @@ int npb_k2_gls(npb_ctx *c, i64 lo, i64 hi)
         NPB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), s));
         NpbTimer tk(c, cls_names[k]);
         int smem = (int)mf_smem_bytes(h_mf[k]);
-        NPB_CUDA(cudaFuncSetAttribute(k_gls_mf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        const bool small = smem <= 9 * 1024;   // small stars: trade registers for resident warps
+        if (small)
+            NPB_CUDA(cudaFuncSetAttribute(k_gls_mf<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        else
+            NPB_CUDA(cudaFuncSetAttribute(k_gls_mf<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int per_sm = (int)((227 * 1024) / (smem + 1024));
         const char *cap = getenv("NPB_GLS_CTAS_PER_SM");
         if (cap && atoi(cap) > 0 && per_sm > atoi(cap)) per_sm = atoi(cap);
@@ -667,7 +691,10 @@ int npb_k2_gls(npb_ctx *c, i64 lo, i64 hi)
         int grid = c->sm_count * per_sm;
         if (grid > count) grid = count;
         NPB_TRY(npb_ensure(&c->gls_ws, &c->gls_ws_cap, sizeof(double) * (size_t)grid * h_mf[k].acap * 2));
-        k_gls_mf<<<grid, 32, smem, s>>>(a, list, count, counter, k, overflow, n_overflow, (double *)c->gls_ws);
+        if (small)
+            k_gls_mf<24><<<grid, 32, smem, s>>>(a, list, count, counter, k, overflow, n_overflow, (double *)c->gls_ws);
+        else
+            k_gls_mf<12><<<grid, 32, smem, s>>>(a, list, count, counter, k, overflow, n_overflow, (double *)c->gls_ws);
         NPB_LAUNCH(c);
         NPB_CUDA(cudaGetLastError());
         tk.stop();
