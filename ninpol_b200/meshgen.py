@@ -242,6 +242,28 @@ def quad_plane(n, perturb=0.0, seed=0, triangles=False):
     return SimpleMesh(pts, [CellBlock("triangle", tris)])
 
 
+def scramble(mesh, seed=0):
+    """Random renumbering of nodes and (per block) of elements, plus a random rotation of every tet's
+    local node order that keeps its orientation: same geometry, but irregular esup / fsup orderings as an
+    unstructured mesh generator would produce.  Fields must be attached afterwards."""
+    rng = np.random.default_rng(seed)
+    npts = len(mesh.points)
+    perm = rng.permutation(npts)            # new id of old node i
+    inv = np.empty(npts, dtype=np.int64)
+    inv[perm] = np.arange(npts)
+    pts = mesh.points[inv]
+    cells = []
+    for blk in mesh.cells:
+        data = perm[blk.data]
+        data = data[rng.permutation(len(data))]
+        if blk.type == "tetra":             # even permutations of (0,1,2,3) keep the orientation
+            even = np.array([[0, 1, 2, 3], [1, 2, 0, 3], [2, 0, 1, 3], [0, 3, 1, 2], [1, 0, 3, 2], [3, 2, 1, 0]])
+            pick = even[rng.integers(0, len(even), size=len(data))]
+            data = np.take_along_axis(data, pick, axis=1)
+        cells.append(CellBlock(blk.type, data))
+    return SimpleMesh(pts, cells)
+
+
 def make_case(kind, n, variable="u", seed=0, neumann_rate=0.5, perturb=None, **kw):
     """Convenience: mesh + fields.  kind in {'hex', 'tet', 'mixed'}."""
     if kind == "hex":
@@ -256,4 +278,6 @@ def make_case(kind, n, variable="u", seed=0, neumann_rate=0.5, perturb=None, **k
         mesh = mixed_box(n, a, b, perturb=0.25 if perturb is None else perturb, seed=seed)
     else:
         raise ValueError(kind)
+    if kw.get("scramble"):
+        mesh = scramble(mesh, seed=seed + 11)
     return attach_fields(mesh, variable=variable, seed=seed + 2, neumann_rate=neumann_rate)

@@ -16,7 +16,7 @@ GRID_SCALARS = ("n_elems", "n_points", "n_faces", "MX_ELEMENTS_PER_POINT", "MX_P
                 "MX_ELEMENTS_PER_FACE", "MX_FACES_PER_POINT")
 GLS_TOL = 1e-12
 
-CASES = [("tet", 7, {}), ("hex", 8, {}), ("mixed", 8, {"a": 2, "b": 4}), ("tet", 14, {}), ("hex", 20, {}),
+CASES = [("tet", 9, {"scramble": True}), ("mixed", 10, {"a": 2, "b": 5, "scramble": True}), ("tet", 7, {}), ("hex", 8, {}), ("mixed", 8, {"a": 2, "b": 4}), ("tet", 14, {}), ("hex", 20, {}),
          ("hex", 6, {"perturb": 0.2}), ("mixed", 12, {"a": 3, "b": 6}), ("tet", 3, {}), ("hex", 1, {}), ("tet", 1, {})]
 
 

@@ -53,7 +53,8 @@ REF = oracle.load_reference()
 
 @pytest.mark.skipif(REF is None, reason="compiled reference (oracle/_ref) not built in this checkout")
 @pytest.mark.parametrize("kind,n,kw", [("tet", 6, {}), ("hex", 7, {}), ("mixed", 8, {"a": 2, "b": 4}), ("hex", 5, {"perturb": 0.2}),
-                                       ("tet", 1, {}), ("hex", 1, {}), ("quad2d", 6, {}), ("tri2d", 6, {"perturb": 0.2})])
+                                       ("tet", 1, {}), ("hex", 1, {}), ("quad2d", 6, {}), ("tri2d", 6, {"perturb": 0.2}),
+                                       ("tet", 6, {"scramble": True}), ("mixed", 8, {"a": 2, "b": 4, "scramble": True})])
 def test_oracle_matches_compiled_reference(kind, n, kw):
     mesh = meshgen.make_case(kind, n, **kw)
     I = REF.Interpolator()
