@@ -206,7 +206,7 @@ def run_reference(args, rank):
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": base["value"], "unit": "nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -382,11 +382,25 @@ def run_ours(args, rank, world):
         except Exception as e:  # the checker must never take the bench down
             line["cpu_baseline"] = {"value": None, "unit": "nodes/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     plumb.close()
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else a library prints on fd 1 (NCCL's version
+    banner, for one) was redirected to stderr in main()."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _JSON_OUT
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
