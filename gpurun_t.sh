@@ -1,2 +1,3 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-for cfg in "tet 69" "hex 64" "mixed 24"; do python tools/run_once.py $cfg gls 3 2>&1 | tail -1 | cut -c1-260; done
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python tools/run_once.py tet 120 gls 3 2>&1 | tail -1 | cut -c1-120
+python tools/run_once.py tet 69 gls 3 2>&1 | tail -1 | cut -c1-120

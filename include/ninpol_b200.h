@@ -125,6 +125,10 @@ int npb_timer_stop(npb_ctx *ctx, double *ms);
 /* Page-locked host memory for the CSR outputs / field inputs (full-rate PCIe copies). */
 int npb_host_alloc(int64_t bytes, void **ptr);
 int npb_host_free(void *ptr);
+/* Page-lock / unlock caller-owned host memory in place (cudaHostRegister), so that the copies made from it
+ * by npb_set_cell_field / npb_set_point_flags / npb_load_mesh run at the PCIe rate without staging. */
+int npb_host_register(void *ptr, int64_t bytes);
+int npb_host_unregister(void *ptr);
 
 #ifdef __cplusplus
 }

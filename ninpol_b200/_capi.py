@@ -41,6 +41,8 @@ _SIGNATURES = {
     "npb_timer_stop": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),
     "npb_host_alloc": (ctypes.c_int, [ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p)]),
     "npb_host_free": (ctypes.c_int, [ctypes.c_void_p]),
+    "npb_host_register": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64]),
+    "npb_host_unregister": (ctypes.c_int, [ctypes.c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -195,6 +197,28 @@ class Context:
         v = ctypes.c_double(0.0)
         check(self.lib.npb_timer_stop(self.handle, ctypes.byref(v)))
         return float(v.value)
+
+
+class HostRegistration:
+    """Keeps a numpy array page-locked in place (cudaHostRegister) for as long as this object lives."""
+
+    def __init__(self, array):
+        self.lib = load_library()
+        self.array = array                       # keeps the memory alive
+        self.ptr = ctypes.c_void_p(array.ctypes.data)
+        check(self.lib.npb_host_register(self.ptr, array.nbytes))
+
+    def release(self):
+        if self.ptr is not None:
+            self.lib.npb_host_unregister(self.ptr)
+            self.ptr = None
+            self.array = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
 
 
 class _PinnedOwner:

@@ -671,6 +671,19 @@ extern "C" int npb_host_free(void *ptr)
     return NPB_OK;
 }
 
+extern "C" int npb_host_register(void *ptr, int64_t bytes)
+{
+    if (!ptr || bytes <= 0) return NPB_ERR_ARG;
+    NPB_CUDA(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+    return NPB_OK;
+}
+
+extern "C" int npb_host_unregister(void *ptr)
+{
+    if (ptr) NPB_CUDA(cudaHostUnregister(ptr));
+    return NPB_OK;
+}
+
 extern "C" int npb_launch_count(npb_ctx *c, int64_t *count)
 {
     if (!c || !count) return NPB_ERR_ARG;

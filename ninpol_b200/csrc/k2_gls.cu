@@ -149,18 +149,67 @@ __device__ __forceinline__ MfWs mf_carve(unsigned char *base, const MfClass &k, 
     return w;
 }
 
+// Closes the holes left by consumed groups in the (global) group arena: live table entries and their
+// blocks slide down in table order, which equals arena order because entries are only ever appended.
+// Keeps the slab region a CTA touches small enough that the resident CTAs' slabs stay in L2 (without it
+// every contribution block ends up written to HBM once: 584 GB per pass over the 50M-tet mesh).
+__device__ void mf_compact(MfWs &w, int &ng, int &top, int lane)
+{
+    int newng = 0, newtop = 0;
+    for (int g0 = 0; g0 < ng; g0 += 32) {
+        int g = g0 + lane;
+        unsigned bal = __ballot_sync(0xffffffffu, g < ng && w.g_nr[g] > 0);
+        while (bal) {
+            int gi = g0 + __ffs(bal) - 1;
+            bal &= bal - 1;
+            u64 mk = w.g_mask[gi];
+            int src = w.g_off[gi], nr = w.g_nr[gi], ld = w.g_ld[gi];
+            int sz = nr * ld;
+            if (src != newtop) {
+                for (int i0 = 0; i0 < sz; i0 += 32) {
+                    int i = i0 + lane;
+                    double v = 0.0;
+                    if (i < sz) v = w.arena[src + i];
+                    __syncwarp();
+                    if (i < sz) w.arena[newtop + i] = v;
+                    __syncwarp();
+                }
+            }
+            if (lane == 0) {
+                w.g_mask[newng] = mk;
+                w.g_off[newng] = newtop;
+                w.g_nr[newng] = (unsigned short)nr;
+                w.g_ld[newng] = (unsigned char)ld;
+            }
+            newtop += sz;
+            newng++;
+        }
+    }
+    __syncwarp();
+    ng = newng;
+    top = newtop;
+}
+
 #define MF_RPL 3   // front rows per lane in the panel factorisation: fronts of up to 96 rows
 
-__device__ __forceinline__ void hh_scalars(double sigma, double x0, double &alpha, double &beta)
+// Householder scalars of one column: alpha = -sign(x0) |x|, beta = 2 / |v|^2 with v = x - alpha e1, and
+// rinv = 1 / alpha (kept on the diagonal of R for the back substitution).  sqrt and 1/alpha come from one
+// rsqrt plus a Newton step instead of the IEEE sqrt and divide sequences.
+__device__ __forceinline__ void hh_scalars(double sigma, double x0, double &alpha, double &beta, double &rinv)
 {
-    if (sigma == 0.0) {
+    if (sigma == 0.0) {   // zero column: identity reflector, zero pivot (NaN takes the normal path and propagates)
         alpha = 0.0;
         beta = 0.0;
+        rinv = 0.0;
         return;
     }
-    double sq = sqrt(sigma);
+    double rs = rsqrt(sigma);
+    double sq = sigma * rs;
+    sq = fma(fma(-sq, sq, sigma), 0.5 * rs, sq);   // sq -> sqrt(sigma) to the last bit or so
+    rs = fma(fma(-sq, rs, 1.0), rs, rs);           // rs -> 1 / sq
     alpha = (x0 >= 0.0) ? -sq : sq;
-    beta = 1.0 / (sigma - x0 * alpha);
+    rinv = (x0 >= 0.0) ? -rs : rs;
+    beta = __drcp_rn(sigma - x0 * alpha);
 }
 
 // returns 0 on success, 1 when the star does not fit this class (caller reroutes it to the dense kernel)
@@ -297,6 +346,11 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
         unsigned key = __reduce_min_sync(FULL, keyA < keyB ? keyA : keyB);
         const int piv = (int)(key & 0xffu);
         const u64 pbit = 1ull << piv;
+        // rescue for stars whose contribution blocks outgrow the slab: close the holes left by consumed groups
+        // (regular stars never get here; compacting eagerly would cut HBM write-back traffic but costs ~9 % time)
+        if (top > (kc.acap / 4) * 3) {
+            mf_compact(w, ng, top, lane);
+        }
         // (b) row groups containing the pivot block
         int nS = 0, rho = 0;
         u64 U = 0;
@@ -336,10 +390,12 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
         if (lane == 0) w.colblk[0] = (unsigned char)piv;
         __syncwarp();
         double *Fm = w.front;
+        const unsigned front_s = (unsigned)__cvta_generic_to_shared(Fm);
         const int ng0 = ng;         // groups appended below are not candidates of this elimination
         int t_next = 0, r_done = 0; // next group of the S list / rows of it already taken
         int carry = 0;              // pivot rows of the previous chunk, kept in front rows [0, carry)
         int npiv = 0;
+        double fri0 = 0.0, fri1 = 0.0, fri2 = 0.0;   // 1 / alpha of the last chunk's pivots
         (void)rho;
         for (bool last = false; !last;) {
             // (d) assemble one chunk: lanes over front columns [pivot block | other blocks ascending | rhs]
@@ -360,10 +416,12 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
                     const double *src = gsrc + sc;
                     double *dst = Fm + rho_c * c + j;
                     if (has) {
+                        unsigned ds = front_s + (unsigned)((rho_c * c + j) * 8);
                         for (int r = 0; r < take; r++) {
-                            cp_async8(dst, src);   // row groups live in global memory: all copies of a chunk in flight at once
+                            // row groups live in global memory: all copies of a chunk are in flight at once
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ds), "l"(src) : "memory");
                             src += ld;
-                            dst += c;
+                            ds += (unsigned)(c * 8);
                         }
                     } else {
                         for (int r = 0; r < take; r++) {
@@ -392,14 +450,14 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
                 a1[q] = ok ? Fm[r * c + 1] : 0.0;
                 a2[q] = ok ? Fm[r * c + 2] : 0.0;
             }
-            double alpha0, beta0, alpha1, beta1, alpha2, beta2, d10, d20, d21;
+            double alpha0, beta0, alpha1, beta1, alpha2, beta2, d10, d20, d21, ri0, ri1, ri2;
             {
                 double sg = 0.0;
 #pragma unroll
                 for (int q = 0; q < MF_RPL; q++) sg += a0[q] * a0[q];
                 sg = warp_sum(sg);
                 double x00 = __shfl_sync(FULL, a0[0], 0);
-                hh_scalars(sg, x00, alpha0, beta0);
+                hh_scalars(sg, x00, alpha0, beta0, ri0);
                 if (lane == 0) a0[0] = x00 - alpha0;                  // a0 now holds v0
                 double t1 = 0.0, t2 = 0.0;
 #pragma unroll
@@ -418,7 +476,7 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
                 for (int q = 0; q < MF_RPL; q++) sg += a1[q] * a1[q];
                 sg = warp_sum(sg);
                 double x11 = __shfl_sync(FULL, a1[0], 1);
-                hh_scalars(sg, x11, alpha1, beta1);
+                hh_scalars(sg, x11, alpha1, beta1, ri1);
                 if (lane == 1) a1[0] = x11 - alpha1;                  // a1 now holds v1
                 if (lane == 0) a2[0] = 0.0;
                 double t2 = 0.0;
@@ -436,7 +494,7 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
                 for (int q = 0; q < MF_RPL; q++) sg += a2[q] * a2[q];
                 sg = warp_sum(sg);
                 double x22 = __shfl_sync(FULL, a2[0], 2);
-                hh_scalars(sg, x22, alpha2, beta2);
+                hh_scalars(sg, x22, alpha2, beta2, ri2);
                 if (lane == 2) a2[0] = x22 - alpha2;                  // a2 now holds v2
                 d10 = 0.0; d20 = 0.0; d21 = 0.0;
 #pragma unroll
@@ -495,6 +553,7 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
                 }
             }
             __syncwarp();
+            fri0 = ri0; fri1 = ri1; fri2 = ri2;
             // (g) rows below the pivot rows (columns of the other blocks + rhs) are appended to the group arena
             //     as a new contribution block; the pivot rows stay in the front for the next chunk, or go to
             //     the R slab after the last one
@@ -530,7 +589,14 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
         }
         for (int t = lane; t < nS; t += 32) w.g_nr[w.s_list[t] & 0xffff] = 0;   // consumed
         (void)ng0;
-        for (int j = lane; j < npiv * c; j += 32) rslab[rtop + j] = Fm[j];
+        // R rows to the slab; the diagonal carries 1 / alpha so that the back substitution has no divisions
+        for (int j = lane; j < npiv * c; j += 32) {
+            double v = Fm[j];
+            if (j == 0) v = fri0;
+            if (j == c + 1) v = fri1;
+            if (j == 2 * c + 2) v = fri2;
+            rslab[rtop + j] = v;
+        }
         if (lane == 0) {
             w.r_mask[nR] = U;
             w.r_off[nR] = rtop;
@@ -578,19 +644,10 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
             p2 += __shfl_xor_sync(FULL, p2, o);
         }
         if (lane == 0) {
-            double g0 = 0.0, g1 = 0.0, g2 = 0.0;
-            if (npiv > 2) {
-                double d = R[2 * c + 2];
-                g2 = d != 0.0 ? (R[2 * c + c - 1] - p2) / d : 0.0;
-            }
-            if (npiv > 1) {
-                double d = R[c + 1];
-                g1 = d != 0.0 ? (R[c + c - 1] - p1 - R[c + 2] * g2) / d : 0.0;
-            }
-            {
-                double d = R[0];
-                g0 = d != 0.0 ? (R[c - 1] - p0 - R[1] * g1 - R[2] * g2) / d : 0.0;
-            }
+            double g0 = 0.0, g1 = 0.0, g2 = 0.0;   // the diagonal of R holds 1 / alpha (0 for a zero pivot)
+            if (npiv > 2) g2 = (R[2 * c + c - 1] - p2) * R[2 * c + 2];
+            if (npiv > 1) g1 = (R[c + c - 1] - p1 - R[c + 2] * g2) * R[c + 1];
+            g0 = (R[c - 1] - p0 - R[1] * g1 - R[2] * g2) * R[0];
             w.gvec[3 * piv] = g0;
             w.gvec[3 * piv + 1] = g1;
             w.gvec[3 * piv + 2] = g2;
