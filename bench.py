@@ -38,8 +38,10 @@ WORKLOADS = {
     "tet7": ("tet", 7, "C1: Kuhn tets n=7 (2,058 cells / 512 nodes)"),
     "hex200": ("hex", 200, "C3: structured hex box 200^3 (8,000,000 cells / 8,120,601 nodes)"),
     "hex128": ("hex", 128, "C2: structured hex box 128^3 (2,097,152 cells)"),
+    "mixed170": ("mixed", 170, "C5: conforming mixed hex/wedge/pyramid/tet box n=170, a=40, b=80 (19.2M cells), 50% Neumann hull nodes"),
+    "mixed60": ("mixed", 60, "mixed hex/wedge/pyramid/tet box n=60 (a=15, b=30)"),
 }
-CPU_SAMPLE = {"tet": ("tet", 40), "hex": ("hex", 64)}
+CPU_SAMPLE = {"tet": ("tet", 40), "hex": ("hex", 64), "mixed": ("mixed", 40)}
 VARIABLE = "u"
 
 
@@ -49,7 +51,8 @@ def log(*a):
 
 def make_mesh(kind, n):
     from ninpol_b200 import meshgen
-    return meshgen.make_case(kind, n, variable=VARIABLE)
+    kw = {"a": (n * 40) // 170, "b": (n * 80) // 170} if kind == "mixed" else {}
+    return meshgen.make_case(kind, n, variable=VARIABLE, **kw)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -46,7 +46,7 @@ def test_cuda_matches_compiled_reference_when_available():
         pytest.skip("oracle/_ref not present on this box")
     import ninpol_b200
     from ninpol_b200 import meshgen
-    mesh = meshgen.make_case("tet", 18)
+    mesh = meshgen.make_case("tet", 40)       # 384,000 cells / 68,921 nodes, 50 % Neumann hull nodes
     R = ref.Interpolator()
     R.load_mesh(mesh_obj=oracle.to_reference_mesh(mesh))
     I = ninpol_b200.Interpolator()
