@@ -34,6 +34,7 @@
 // overflow detected at run time) go to the dense global-memory kernel of k2_gls_dense.cu.  The kernel is
 // latency / issue bound on this bookkeeping, not FP64 or HBM bound (profiles/).
 #include <stdlib.h>
+#include <string.h>
 #include "gls_common.cuh"
 
 typedef unsigned long long u64;
@@ -50,13 +51,12 @@ struct MfClass {
 #define MF_CLASS_TABLE {{0, 0, 0, 0}, {384, 8, 14, 3072}, {640, 12, 22, 6144}, {768, 16, 30, 8192}, {1408, 24, 40, 12288}, \
                         {1536, 32, 56, 18432}, {2560, 48, 80, 32768}, {4096, 64, 112, 49152}, {0, 0, 0, 0}}
 __constant__ MfClass c_mf[MF_NCLASS] = MF_CLASS_TABLE;
-static const MfClass h_mf[MF_NCLASS] = MF_CLASS_TABLE;
+static MfClass h_mf[MF_NCLASS] = MF_CLASS_TABLE;
 
 __host__ __device__ __forceinline__ int mf_ngcap(const MfClass &k) { return ((2 * k.ecap + k.fcap_f + 7) / 8) * 8; }
-__host__ __device__ __forceinline__ int mf_mcap(const MfClass &k) { int m = k.ecap + 4 * k.fcap_f; return m < 96 ? m : 96; }
 __host__ __device__ __forceinline__ size_t mf_smem_bytes(const MfClass &k)
 {
-    size_t d = (size_t)k.fcap + 4 * (size_t)mf_mcap(k) + 6 * (size_t)k.ecap;  // front, vbuf[.][4], gvec, dvec
+    size_t d = (size_t)k.fcap + 6 * (size_t)k.ecap;  // front, gvec, dvec
     size_t b = d * 8 + (size_t)mf_ngcap(k) * (8 + 4 + 2 + 1) + (size_t)k.ecap * (8 + 4 + 4);   // group table, R table
     b += (size_t)k.ecap * 4 + MF_SCAP * 4 + 64;                             // es, S list, colblk
     return (b + 15) & ~(size_t)15;
@@ -117,7 +117,7 @@ __device__ __forceinline__ int nth_set_bit(u64 m, int n)  // index of the n-th (
 struct MfWs {
     double *arena;   // global: row groups (original rows, contribution blocks), append-only
     double *front;   // shared: the dense front being factored
-    double *vbuf, *gvec, *dvec;
+    double *gvec, *dvec;
     u64 *g_mask, *r_mask;
     int *g_off, *r_off, *r_meta;   // r_meta = piv | npiv << 8 | c << 16
     unsigned short *g_nr;
@@ -133,8 +133,7 @@ __device__ __forceinline__ MfWs mf_carve(unsigned char *base, const MfClass &k, 
     int ng = mf_ngcap(k);
     w.arena = garena;
     w.front = (double *)base;
-    w.vbuf = w.front + k.fcap;                  // [mcap][4]: the three Householder vectors of a front
-    w.gvec = w.vbuf + 4 * mf_mcap(k);
+    w.gvec = w.front + k.fcap;
     w.dvec = w.gvec + 3 * k.ecap;
     w.g_mask = (u64 *)(w.dvec + 3 * k.ecap);
     w.r_mask = w.g_mask + ng;
@@ -213,7 +212,7 @@ __device__ __forceinline__ void hh_scalars(double sigma, double x0, double &alph
 }
 
 // returns 0 on success, 1 when the star does not fit this class (caller reroutes it to the dense kernel)
-__device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfClass &kc, double *rslab, double *garena)
+__device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfClass &kc, double *rslab, double *garena, int flags)
 {
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
@@ -338,6 +337,202 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
     u64 alive = (E >= 64) ? ~0ull : ((1ull << E) - 1ull);
     int nR = 0, rtop = 0;   // R rows written so far (entries / doubles in the global slab)
 
+    // ---- leaf fronts, one per LANE ----
+    // A block none of whose neighbours has been eliminated has a front made of original rows only: its
+    // element row and its <= 3 face groups (3 rows coupling it to one neighbour, or one Neumann row),
+    // 10 x (3 + 3 nn + 1) with a fixed sparsity.  Such blocks are pairwise independent when no two are
+    // adjacent, so a greedy independent set of them (12 of the 24 tets around an interior node of the
+    // Kuhn mesh) is eliminated at once: lane b factors the front of block b entirely in registers and
+    // writes its 3 rows of R and its 7-row contribution block straight to the slabs.
+    if (!(flags & 1) && ng - E <= 64) {
+        u64 *fmask = w.r_mask;   // free until the first rows of R are recorded
+        for (int i = lane; i < E; i += 32) fmask[i] = 0ull;
+        __syncwarp();
+        for (int g = E + lane; g < ng; g += 32) {   // atomicOr: the result does not depend on the order
+            u64 mk = w.g_mask[g];
+            const u64 bit = 1ull << (g - E);
+            atomicOr((unsigned long long *)&fmask[__ffsll((long long)mk) - 1], bit);
+            mk &= mk - 1;
+            if (mk) atomicOr((unsigned long long *)&fmask[__ffsll((long long)mk) - 1], bit);
+        }
+        __syncwarp();
+        const int b = lane;
+        u64 fm = (b < E) ? fmask[b] : 0ull;
+        __syncwarp();
+        const int nf = __popcll(fm);
+        bool elig = b < E && nf <= 3;
+        int gk[3], nbk[3], offk[3];
+        bool valid[3], intr[3];
+        u64 Upl = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            valid[k] = elig && k < nf;
+            gk[k] = E + (valid[k] ? __ffsll((long long)fm) - 1 : 0);
+            fm &= fm - 1;
+            const u64 other = valid[k] ? (w.g_mask[gk[k]] & ~(1ull << b)) : 0ull;
+            intr[k] = other != 0;
+            nbk[k] = intr[k] ? __ffsll((long long)other) - 1 : 0;
+            offk[k] = valid[k] ? w.g_off[gk[k]] : 0;
+            if (intr[k] && ((Upl >> nbk[k]) & 1ull)) elig = false;   // two faces shared with one neighbour
+            if (intr[k]) Upl |= 1ull << nbk[k];
+        }
+        // greedy independent set in index order (what minimum degree picks on a closed star)
+        unsigned rem = __ballot_sync(FULL, elig), chosen = 0;
+        {
+            const unsigned nbm = (unsigned)Upl;
+            while (rem) {
+                const int bb = __ffs(rem) - 1;
+                chosen |= 1u << bb;
+                rem &= ~(__shfl_sync(FULL, nbm, bb) | (1u << bb));
+            }
+        }
+        const bool mine = (chosen >> lane) & 1u;
+        const int nn = __popcll(Upl);
+        const int c = 3 * nn + 4, cw = c - 3;
+        const int cbsz = (mine && nn > 0) ? 7 * cw : 0, rsz = mine ? 3 * c : 0;
+        int cb_incl = cbsz, r_incl = rsz;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t1 = __shfl_up_sync(FULL, cb_incl, o), t2 = __shfl_up_sync(FULL, r_incl, o);
+            if (lane >= o) { cb_incl += t1; r_incl += t2; }
+        }
+        const int cb_tot = __shfl_sync(FULL, cb_incl, 31), r_tot = __shfl_sync(FULL, r_incl, 31);
+        const unsigned hascb = __ballot_sync(FULL, mine && nn > 0);
+        if (ng + __popc(hascb) > ngcap || top + cb_tot > kc.acap || rtop + r_tot > kc.acap) return 1;
+        if (mine) {
+            const unsigned below = (1u << lane) - 1u;
+            double *Rr = rslab + rtop + (r_incl - rsz);
+            double *CB = w.arena + top + (cb_incl - cbsz);
+            double a0[10], a1[10], a2[10];
+            a0[0] = w.dvec[3 * b]; a1[0] = w.dvec[3 * b + 1]; a2[0] = w.dvec[3 * b + 2];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                // own columns come second when the neighbour has the smaller index
+                const double *src = w.arena + offk[k] + ((intr[k] && nbk[k] < b) ? 3 : 0);
+                const int ld = intr[k] ? 7 : 4;
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+                    const bool has = valid[k] && (intr[k] || r == 0);
+                    a0[1 + 3 * k + r] = has ? src[r * ld] : 0.0;
+                    a1[1 + 3 * k + r] = has ? src[r * ld + 1] : 0.0;
+                    a2[1 + 3 * k + r] = has ? src[r * ld + 2] : 0.0;
+                }
+            }
+            double alpha0, beta0, alpha1, beta1, alpha2, beta2, ri0, ri1, ri2;
+            {
+                double sg = 0.0;
+#pragma unroll
+                for (int q = 0; q < 10; q++) sg += a0[q] * a0[q];
+                hh_scalars(sg, a0[0], alpha0, beta0, ri0);
+                a0[0] -= alpha0;
+                double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+                for (int q = 0; q < 10; q++) { t1 += a0[q] * a1[q]; t2 += a0[q] * a2[q]; }
+                t1 *= beta0; t2 *= beta0;
+#pragma unroll
+                for (int q = 0; q < 10; q++) { a1[q] -= t1 * a0[q]; a2[q] -= t2 * a0[q]; }
+            }
+            const double r01 = a1[0], r02 = a2[0];
+            a1[0] = 0.0; a2[0] = 0.0;
+            {
+                double sg = 0.0;
+#pragma unroll
+                for (int q = 1; q < 10; q++) sg += a1[q] * a1[q];
+                hh_scalars(sg, a1[1], alpha1, beta1, ri1);
+                a1[1] -= alpha1;
+                double t2 = 0.0;
+#pragma unroll
+                for (int q = 1; q < 10; q++) t2 += a1[q] * a2[q];
+                t2 *= beta1;
+#pragma unroll
+                for (int q = 1; q < 10; q++) a2[q] -= t2 * a1[q];
+            }
+            const double r12 = a2[1];
+            a2[1] = 0.0;
+            double d10 = 0.0, d20 = 0.0, d21 = 0.0;
+            {
+                double sg = 0.0;
+#pragma unroll
+                for (int q = 2; q < 10; q++) sg += a2[q] * a2[q];
+                hh_scalars(sg, a2[2], alpha2, beta2, ri2);
+                a2[2] -= alpha2;
+#pragma unroll
+                for (int q = 0; q < 10; q++) { d10 += a1[q] * a0[q]; d20 += a2[q] * a0[q]; d21 += a2[q] * a1[q]; }
+            }
+            Rr[0] = ri0; Rr[1] = r01; Rr[2] = r02;
+            Rr[c] = 0.0; Rr[c + 1] = ri1; Rr[c + 2] = r12;
+            Rr[2 * c] = 0.0; Rr[2 * c + 1] = 0.0; Rr[2 * c + 2] = ri2;
+            // the neighbours' columns: three nonzeros each before the reflections, dense after
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                if (!intr[k]) continue;
+                const int slot = 1 + __popcll(Upl & ((1ull << nbk[k]) - 1ull));
+                const double *src = w.arena + offk[k] + ((nbk[k] < b) ? 0 : 3);
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    const double n0 = src[q], n1 = src[7 + q], n2 = src[14 + q];
+                    const double w0 = a0[1 + 3 * k] * n0 + a0[2 + 3 * k] * n1 + a0[3 + 3 * k] * n2;
+                    const double w1 = a1[1 + 3 * k] * n0 + a1[2 + 3 * k] * n1 + a1[3 + 3 * k] * n2;
+                    const double w2 = a2[1 + 3 * k] * n0 + a2[2 + 3 * k] * n1 + a2[3 + 3 * k] * n2;
+                    const double s0 = beta0 * w0;
+                    const double s1 = beta1 * (w1 - d10 * s0);
+                    const double s2 = beta2 * (w2 - d20 * s0 - d21 * s1);
+                    double *rcol = Rr + 3 * slot + q, *ccol = CB + 3 * (slot - 1) + q;
+#pragma unroll
+                    for (int r = 0; r < 10; r++) {
+                        double o = (r == 1 + 3 * k) ? n0 : (r == 2 + 3 * k) ? n1 : (r == 3 + 3 * k) ? n2 : 0.0;
+                        double v = o - (a0[r] * s0 + a1[r] * s1 + a2[r] * s2);
+                        if (r < 3) rcol[r * c] = v;
+                        else ccol[(r - 3) * cw] = v;
+                    }
+                }
+            }
+            {   // right-hand side: e_0 before the reflections
+                const double s0 = beta0 * a0[0];
+                const double s1 = beta1 * (-d10 * s0);
+                const double s2 = beta2 * (-d20 * s0 - d21 * s1);
+#pragma unroll
+                for (int r = 0; r < 10; r++) {
+                    double v = (r == 0 ? 1.0 : 0.0) - (a0[r] * s0 + a1[r] * s1 + a2[r] * s2);
+                    if (r < 3) Rr[r * c + c - 1] = v;
+                    else if (nn > 0) CB[(r - 3) * cw + cw - 1] = v;
+                }
+            }
+            // tables: consumed groups, the new contribution block, the rows of R
+            w.g_nr[b] = 0;
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                if (valid[k]) w.g_nr[gk[k]] = 0;
+            if (nn > 0) {
+                const int gi = ng + __popc(hascb & below);
+                w.g_mask[gi] = Upl;
+                w.g_off[gi] = top + (cb_incl - cbsz);
+                w.g_nr[gi] = 7;
+                w.g_ld[gi] = (unsigned char)cw;
+            }
+            const int ri = nR + __popc(chosen & below);
+            w.r_mask[ri] = Upl | (1ull << b);
+            w.r_off[ri] = rtop + (r_incl - rsz);
+            w.r_meta[ri] = b | (3 << 8) | (c << 16);
+        }
+        __syncwarp();
+        // adjacency: the neighbours of every eliminated leaf become a clique
+        const u64 Ufull = mine ? (Upl | (1ull << b)) : 0ull;
+        for (unsigned cm = chosen; cm; cm &= cm - 1) {
+            const int bb = __ffs(cm) - 1;
+            const u64 Ub = __shfl_sync(FULL, Ufull, bb);
+            const u64 keep = ~(1ull << bb);
+            if (((Ub >> lane) & 1ull) && lane != bb) adjA = (adjA | Ub) & keep;
+            if ((Ub >> (lane + 32)) & 1ull) adjB = (adjB | Ub) & keep;
+        }
+        alive &= ~(u64)chosen;
+        top += cb_tot;
+        ng += __popc(hascb);
+        nR += __popc(chosen);
+        rtop += r_tot;
+        __syncwarp();
+    }
+
     // ---- elimination ----
     while (alive) {
         // (a) minimum-degree pivot block
@@ -382,7 +577,9 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
         const u64 Up = U & ~pbit;
         const int c = 3 * __popcll(U) + 1;
         // (c) capacity checks: group table, R slab; the front is processed in chunks of at most `rcap` rows
-        const int rcap = min(32 * MF_RPL, min(mf_mcap(kc), kc.fcap / c));
+        const int ld = (c + 1) & ~1;   // even row stride: rows stay 16-byte aligned for the v loads
+        const int rcap = min(32 * MF_RPL, kc.fcap / ld);
+        const int La = c > 16 ? 32 : c > 8 ? 16 : c > 4 ? 8 : 4, Ga = 32 / La;   // assembly: lanes per front row
         if (nS > MF_SCAP || rcap < 8 || rtop + 3 * c > kc.acap) return 1;
         // block id of every column slot: slot 0 = pivot, then the other blocks ascending
         if ((Up >> lane) & 1ull) w.colblk[1 + __popcll(Up & ((1ull << lane) - 1ull))] = (unsigned char)lane;
@@ -403,30 +600,32 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
             while (t_next < nS && rho_c < rcap) {
                 const int g = w.s_list[t_next] & 0xffff;
                 const u64 mk = w.g_mask[g];
-                const int nr = w.g_nr[g], ld = w.g_ld[g];
+                const int nr = w.g_nr[g], gld = w.g_ld[g];
                 const int take = min(nr - r_done, rcap - rho_c);
-                const double *gsrc = w.arena + w.g_off[g] + r_done * ld;
+                const double *gsrc = w.arena + w.g_off[g] + r_done * gld;
+                // fronts of <= 16 columns: La lanes per row, Ga rows per step
                 for (int j0 = 0; j0 < c; j0 += 32) {
-                    int j = j0 + lane;
+                    const int j = (La == 32) ? j0 + lane : (lane & (La - 1));
+                    const int r0 = (La == 32) ? 0 : lane / La;
                     if (j >= c) continue;
                     const bool is_rhs = (j == c - 1);
                     const int blk = is_rhs ? 0 : w.colblk[j / 3];
                     const bool has = is_rhs || ((mk >> blk) & 1ull);
                     const int sc = is_rhs ? 3 * __popcll(mk) : 3 * __popcll(mk & ((1ull << blk) - 1ull)) + j % 3;
-                    const double *src = gsrc + sc;
-                    double *dst = Fm + rho_c * c + j;
                     if (has) {
-                        unsigned ds = front_s + (unsigned)((rho_c * c + j) * 8);
-                        for (int r = 0; r < take; r++) {
+                        const double *src = gsrc + sc + r0 * gld;
+                        unsigned ds = front_s + (unsigned)(((rho_c + r0) * ld + j) * 8);
+                        for (int r = r0; r < take; r += Ga) {
                             // row groups live in global memory: all copies of a chunk are in flight at once
                             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ds), "l"(src) : "memory");
-                            src += ld;
-                            ds += (unsigned)(c * 8);
+                            src += Ga * gld;
+                            ds += (unsigned)(Ga * ld * 8);
                         }
                     } else {
-                        for (int r = 0; r < take; r++) {
+                        double *dst = Fm + (rho_c + r0) * ld + j;
+                        for (int r = r0; r < take; r += Ga) {
                             *dst = 0.0;
-                            dst += c;
+                            dst += Ga * ld;
                         }
                     }
                 }
@@ -446,9 +645,9 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
             for (int q = 0; q < MF_RPL; q++) {
                 int r = lane + 32 * q;
                 bool ok = r < rho_c;
-                a0[q] = ok ? Fm[r * c + 0] : 0.0;
-                a1[q] = ok ? Fm[r * c + 1] : 0.0;
-                a2[q] = ok ? Fm[r * c + 2] : 0.0;
+                a0[q] = ok ? Fm[r * ld + 0] : 0.0;
+                a1[q] = ok ? Fm[r * ld + 1] : 0.0;
+                a2[q] = ok ? Fm[r * ld + 2] : 0.0;
             }
             double alpha0, beta0, alpha1, beta1, alpha2, beta2, d10, d20, d21, ri0, ri1, ri2;
             {
@@ -506,36 +705,72 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
                     d21 += __shfl_xor_sync(FULL, d21, o);
                 }
             }
-            // v vectors to shared memory as [row][4]; the pivot rows' panel entries of R
+            // the Householder vectors overwrite the panel columns of the front (LAPACK style); the pivot rows'
+            // panel entries of R are put back after the update
 #pragma unroll
             for (int q = 0; q < MF_RPL; q++) {
                 int r = lane + 32 * q;
                 if (r < rho_c) {
-                    double2 *vp = reinterpret_cast<double2 *>(w.vbuf + 4 * r);
-                    vp[0] = make_double2(a0[q], a1[q]);
-                    vp[1] = make_double2(a2[q], 0.0);
+                    *reinterpret_cast<double2 *>(Fm + r * ld) = make_double2(a0[q], a1[q]);
+                    Fm[r * ld + 2] = a2[q];
                 }
             }
-            if (lane == 0) {
-                Fm[0] = alpha0; Fm[1] = r01; Fm[2] = r02;
-                if (rho_c > 1) { Fm[c] = 0.0; Fm[c + 1] = alpha1; Fm[c + 2] = r12; }
-                if (rho_c > 2) { Fm[2 * c] = 0.0; Fm[2 * c + 1] = 0.0; Fm[2 * c + 2] = alpha2; }
-            }
             __syncwarp();
-            // (f) apply the three reflections to the other columns: two passes over the rows
+            // (f) apply the three reflections to the other columns: two passes over the rows.  Narrow fronts
+            //     (<= 16 other columns: the tall-skinny end game) split the rows over 2..32 lane groups
+            const int cw3 = c - 3;
+            // lanes per group: the power of two covering the columns; G = 32 / L groups take rows g, g + G, ...
+            const int L = cw3 > 16 ? 32 : cw3 > 8 ? 16 : cw3 > 4 ? 8 : cw3 > 2 ? 4 : cw3 > 1 ? 2 : 1;
+            if (L < 32 && cw3 > 0) {
+                const int G = 32 / L, grp = lane / L, jl = lane & (L - 1);
+                const bool act = jl < cw3;
+                const int j = 3 + (act ? jl : 0);
+                const int step = G * ld;
+                double w0 = 0.0, w1 = 0.0, w2 = 0.0;
+                {
+                    const double *vp = Fm + grp * ld;
+#pragma unroll 4
+                    for (int r = grp; r < rho_c; r += G) {
+                        double f = vp[j];
+                        double2 va = *reinterpret_cast<const double2 *>(vp);
+                        double vc = vp[2];
+                        w0 += va.x * f; w1 += va.y * f; w2 += vc * f;
+                        vp += step;
+                    }
+                }
+                for (int o = L; o < 32; o <<= 1) {
+                    w0 += __shfl_xor_sync(FULL, w0, o);
+                    w1 += __shfl_xor_sync(FULL, w1, o);
+                    w2 += __shfl_xor_sync(FULL, w2, o);
+                }
+                double s0 = beta0 * w0;
+                double s1 = beta1 * (w1 - d10 * s0);
+                double s2 = beta2 * (w2 - d20 * s0 - d21 * s1);
+                if (act) {
+                    double *vp = Fm + grp * ld;
+#pragma unroll 4
+                    for (int r = grp; r < rho_c; r += G) {
+                        double2 va = *reinterpret_cast<const double2 *>(vp);
+                        double vc = vp[2];
+                        vp[j] = vp[j] - (va.x * s0 + va.y * s1 + vc * s2);
+                        vp += step;
+                    }
+                }
+            } else
             for (int j0 = 3; j0 < c; j0 += 32) {
                 int j = j0 + lane;
                 if (j >= c) continue;
                 double w0 = 0.0, w1 = 0.0, w2 = 0.0;
                 {
                     const double *fp = Fm + j;
-                    const double2 *vp = reinterpret_cast<const double2 *>(w.vbuf);
+                    const double *vp = Fm;
 #pragma unroll 4
                     for (int r = 0; r < rho_c; r++) {
                         double f = *fp;
-                        double2 va = vp[0], vb = vp[1];
-                        w0 += va.x * f; w1 += va.y * f; w2 += vb.x * f;
-                        fp += c; vp += 2;
+                        double2 va = *reinterpret_cast<const double2 *>(vp);
+                        double vc = vp[2];
+                        w0 += va.x * f; w1 += va.y * f; w2 += vc * f;
+                        fp += ld; vp += ld;
                     }
                 }
                 double s0 = beta0 * w0;
@@ -543,14 +778,21 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
                 double s2 = beta2 * (w2 - d20 * s0 - d21 * s1);
                 {
                     double *fp = Fm + j;
-                    const double2 *vp = reinterpret_cast<const double2 *>(w.vbuf);
+                    const double *vp = Fm;
 #pragma unroll 4
                     for (int r = 0; r < rho_c; r++) {
-                        double2 va = vp[0], vb = vp[1];
-                        *fp = *fp - (va.x * s0 + va.y * s1 + vb.x * s2);
-                        fp += c; vp += 2;
+                        double2 va = *reinterpret_cast<const double2 *>(vp);
+                        double vc = vp[2];
+                        *fp = *fp - (va.x * s0 + va.y * s1 + vc * s2);
+                        fp += ld; vp += ld;
                     }
                 }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                Fm[0] = alpha0; Fm[1] = r01; Fm[2] = r02;
+                if (rho_c > 1) { Fm[ld] = 0.0; Fm[ld + 1] = alpha1; Fm[ld + 2] = r12; }
+                if (rho_c > 2) { Fm[2 * ld] = 0.0; Fm[2 * ld + 1] = 0.0; Fm[2 * ld + 2] = alpha2; }
             }
             __syncwarp();
             fri0 = ri0; fri1 = ri1; fri2 = ri2;
@@ -563,14 +805,26 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
             if (keep) {
                 const int cw = c - 3;
                 if (ng + 1 > ngcap || top + left * cw > kc.acap) return 1;
+                if (L < 32) {   // same lane groups as the update: G rows per step
+                    const int G = 32 / L, grp = lane / L, jl = lane & (L - 1);
+                    if (jl < cw) {
+                        const double *src = Fm + (npiv + grp) * ld + 3 + jl;
+                        double *dst = w.arena + top + grp * cw + jl;
+                        for (int r = grp; r < left; r += G) {
+                            *dst = *src;
+                            src += G * ld;
+                            dst += G * cw;
+                        }
+                    }
+                } else
                 for (int j0 = 0; j0 < cw; j0 += 32) {
                     int j = j0 + lane;
                     if (j < cw) {
-                        const double *src = Fm + npiv * c + 3 + j;
+                        const double *src = Fm + npiv * ld + 3 + j;
                         double *dst = w.arena + top + j;
                         for (int r = 0; r < left; r++) {
                             *dst = *src;
-                            src += c;
+                            src += ld;
                             dst += cw;
                         }
                     }
@@ -590,12 +844,14 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
         for (int t = lane; t < nS; t += 32) w.g_nr[w.s_list[t] & 0xffff] = 0;   // consumed
         (void)ng0;
         // R rows to the slab; the diagonal carries 1 / alpha so that the back substitution has no divisions
-        for (int j = lane; j < npiv * c; j += 32) {
-            double v = Fm[j];
-            if (j == 0) v = fri0;
-            if (j == c + 1) v = fri1;
-            if (j == 2 * c + 2) v = fri2;
-            rslab[rtop + j] = v;
+        for (int j = lane; j < c; j += 32) {
+            double v0 = Fm[j], v1 = Fm[ld + j], v2 = Fm[2 * ld + j];
+            if (j == 0) v0 = fri0;
+            if (j == 1) v1 = fri1;
+            if (j == 2) v2 = fri2;
+            rslab[rtop + j] = v0;
+            if (npiv > 1) rslab[rtop + c + j] = v1;
+            if (npiv > 2) rslab[rtop + 2 * c + j] = v2;
         }
         if (lane == 0) {
             w.r_mask[nR] = U;
@@ -659,15 +915,15 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
     double part = 0.0;
     for (int i = lane; i < E; i += 32) {
         double ri = 1.0 - (w.dvec[3 * i] * w.gvec[3 * i] + w.dvec[3 * i + 1] * w.gvec[3 * i + 1] + w.dvec[3 * i + 2] * w.gvec[3 * i + 2]);
-        w.vbuf[i] = ri;
+        w.front[i] = ri;
         part += ri;
     }
     double tot = warp_sum(part);
     __syncwarp();
-    double nv = neu ? w.vbuf[E - 1] / tot : 0.0;   // gls.pyx:470-472 (Q3)
+    double nv = neu ? w.front[E - 1] / tot : 0.0;   // gls.pyx:470-472 (Q3)
     int cnt = 0;
     for (int i = lane; i < E; i += 32) {
-        double v = w.vbuf[i] / tot + nv;           // interpolator.pyx:618 (Q4)
+        double v = w.front[i] / tot + nv;           // interpolator.pyx:618 (Q4)
         wo[i] = v;
         cnt += (v != 0.0) ? 1 : 0;
     }
@@ -685,7 +941,7 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
 template <int MINBLOCKS>
 __global__ void __launch_bounds__(32, MINBLOCKS)
 k_gls_mf(GlsArgs a, const int32_t *__restrict__ list, int count, int *__restrict__ counter, int klass,
-         int32_t *__restrict__ overflow, int *__restrict__ n_overflow, double *__restrict__ slabs)
+         int32_t *__restrict__ overflow, int *__restrict__ n_overflow, double *__restrict__ slabs, int flags)
 {
     extern __shared__ __align__(16) unsigned char smem_mf[];
     const MfClass kc = c_mf[klass];
@@ -697,7 +953,7 @@ k_gls_mf(GlsArgs a, const int32_t *__restrict__ list, int count, int *__restrict
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= count) break;
         int p = list[i];
-        int rc = mf_node(a, p, smem_mf, kc, rslab, garena);
+        int rc = mf_node(a, p, smem_mf, kc, rslab, garena, flags);
         __syncwarp();
         if (rc != 0 && threadIdx.x == 0) overflow[atomicAdd(n_overflow, 1)] = p;
     }
@@ -724,6 +980,22 @@ int npb_k2_gls(npb_ctx *c, i64 lo, i64 hi)
     const char *force = getenv("NPB_FORCE_GLS_DENSE");   // tests: exercise the dense fallback kernel
     k_gls_classify<<<npb_blocks(nloc, 256), 256, 0, s>>>(a, lo, hi, cls, (force && force[0] == '1') ? 1 : 0);
     NPB_LAUNCH(c);
+    {   // experiments: NPB_GLS_FCAP="class:doubles[,class:doubles...]" overrides the front sizes
+        static bool once = false;
+        const char *fo = getenv("NPB_GLS_FCAP");
+        if (!once && fo) {
+            once = true;
+            for (const char *q = fo; q && *q;) {
+                int k = atoi(q);
+                const char *col = strchr(q, ':');
+                if (!col) break;
+                if (k >= 1 && k < MF_NCLASS - 1) h_mf[k].fcap = atoi(col + 1);
+                q = strchr(col, ',');
+                if (q) q++;
+            }
+            NPB_CUDA(cudaMemcpyToSymbol(c_mf, h_mf, sizeof(h_mf)));
+        }
+    }
     float main_ms = 0.f;
     static const char *cls_names[MF_NCLASS] = {"", "k2_gls_c1", "k2_gls_c2", "k2_gls_c3", "k2_gls_c4", "k2_gls_c5", "k2_gls_c6", "k2_gls_c7", "k2_gls_dense"};
     for (int k = 1; k < MF_NCLASS; k++) c->timings.erase(cls_names[k]);
@@ -736,22 +1008,31 @@ int npb_k2_gls(npb_ctx *c, i64 lo, i64 hi)
         NPB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), s));
         NpbTimer tk(c, cls_names[k]);
         int smem = (int)mf_smem_bytes(h_mf[k]);
-        const bool small = smem <= 9 * 1024;   // small stars: trade registers for resident warps
-        if (small)
-            NPB_CUDA(cudaFuncSetAttribute(k_gls_mf<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        else
-            NPB_CUDA(cudaFuncSetAttribute(k_gls_mf<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        // resident warps per SM are bounded by shared memory; the launch bound follows it so that small
+        // stars trade registers for residency (24: 80 registers, 16: 128, 12: 168)
         int per_sm = (int)((227 * 1024) / (smem + 1024));
+        const char *noleaf = getenv("NPB_GLS_NO_LEAF");   // tests / A-B timing: every front through the general loop
+        const int mf_flags = (noleaf && noleaf[0] == '1') ? 1 : 0;
         const char *cap = getenv("NPB_GLS_CTAS_PER_SM");
         if (cap && atoi(cap) > 0 && per_sm > atoi(cap)) per_sm = atoi(cap);
         if (per_sm > 32) per_sm = 32;
+        int variant = per_sm >= 16 ? 16 : 12;   // 24 (80 registers) spills the leaf fronts: only on request
+        const char *var = getenv("NPB_GLS_VARIANT");
+        if (var && (atoi(var) == 12 || atoi(var) == 16 || atoi(var) == 24)) variant = atoi(var);
+        if (per_sm > 65536 / (32 * (variant == 24 ? 80 : variant == 16 ? 128 : 168))) per_sm = 65536 / (32 * (variant == 24 ? 80 : variant == 16 ? 128 : 168));
         int grid = c->sm_count * per_sm;
         if (grid > count) grid = count;
         NPB_TRY(npb_ensure(&c->gls_ws, &c->gls_ws_cap, sizeof(double) * (size_t)grid * h_mf[k].acap * 2));
-        if (small)
-            k_gls_mf<24><<<grid, 32, smem, s>>>(a, list, count, counter, k, overflow, n_overflow, (double *)c->gls_ws);
-        else
-            k_gls_mf<12><<<grid, 32, smem, s>>>(a, list, count, counter, k, overflow, n_overflow, (double *)c->gls_ws);
+#define MF_LAUNCH(V)                                                                                              \
+    do {                                                                                                          \
+        NPB_CUDA(cudaFuncSetAttribute(k_gls_mf<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));           \
+        k_gls_mf<V><<<grid, 32, smem, s>>>(a, list, count, counter, k, overflow, n_overflow, (double *)c->gls_ws, \
+                                           mf_flags);                                                             \
+    } while (0)
+        if (variant == 24) MF_LAUNCH(24);
+        else if (variant == 16) MF_LAUNCH(16);
+        else MF_LAUNCH(12);
+#undef MF_LAUNCH
         NPB_LAUNCH(c);
         NPB_CUDA(cudaGetLastError());
         tk.stop();
