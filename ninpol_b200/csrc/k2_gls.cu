@@ -189,6 +189,35 @@ __device__ void mf_compact(MfWs &w, int &ng, int &top, int lane)
     top = newtop;
 }
 
+// rows x cw block of the front (row stride sld) -> contiguous rows in the group arena; narrow blocks put
+// several rows on the 32 lanes
+__device__ __forceinline__ void mf_store_cb(const double *src, int sld, int rows, int cw, double *dst, int lane)
+{
+    const int L = cw > 16 ? 32 : cw > 8 ? 16 : cw > 4 ? 8 : cw > 2 ? 4 : cw > 1 ? 2 : 1;
+    if (L < 32) {
+        const int G = 32 / L, grp = lane / L, jl = lane & (L - 1);
+        if (jl < cw) {
+            src += grp * sld + jl;
+            dst += grp * cw + jl;
+            for (int r = grp; r < rows; r += G) {
+                *dst = *src;
+                src += G * sld;
+                dst += G * cw;
+            }
+        }
+    } else {
+        for (int j = lane; j < cw; j += 32) {
+            const double *sp = src + j;
+            double *dp = dst + j;
+            for (int r = 0; r < rows; r++) {
+                *dp = *sp;
+                sp += sld;
+                dp += cw;
+            }
+        }
+    }
+}
+
 #define MF_RPL 3   // front rows per lane in the panel factorisation: fronts of up to 96 rows
 
 // Householder scalars of one column: alpha = -sign(x0) |x|, beta = 2 / |v|^2 with v = x - alpha e1, and
@@ -336,6 +365,7 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
     }
     u64 alive = (E >= 64) ? ~0ull : ((1ull << E) - 1ull);
     int nR = 0, rtop = 0;   // R rows written so far (entries / doubles in the global slab)
+    int n_leaf = 0;         // the first n_leaf entries of the R table are leaf fronts
 
     // ---- leaf fronts, one per LANE ----
     // A block none of whose neighbours has been eliminated has a front made of original rows only: its
@@ -529,11 +559,18 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
         top += cb_tot;
         ng += __popc(hascb);
         nR += __popc(chosen);
+        n_leaf = nR;
         rtop += r_tot;
         __syncwarp();
     }
 
     // ---- elimination ----
+    // The contribution block of a front stays where it is (rows >= 3, columns >= 3 of the front) until the
+    // next pivot is known: when that pivot is the block's first column and brings no new column - every
+    // step of the dense end game, where the remaining blocks form a clique - the next front is built in
+    // place around it and only the new rows are fetched; otherwise it is flushed to the group arena.
+    int ch_rows = 0, ch_off = 0, ch_ld = 0;
+    u64 ch_mask = 0;
     while (alive) {
         // (a) minimum-degree pivot block
         unsigned keyA = ((alive >> lane) & 1ull) ? (unsigned)((__popcll(adjA) << 8) | lane) : 0xffffffffu;
@@ -574,23 +611,52 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
             rho += __shfl_sync(FULL, incl, 31);
             U |= warp_or64(in ? mk : 0ull);
         }
+        bool inplace = false;
+        if (ch_rows > 0) {
+            const bool has = (ch_mask & pbit) != 0;
+            if (has && (ch_mask & (pbit - 1ull)) == 0 && (U & ~ch_mask) == 0 && nS <= MF_SCAP)
+                inplace = ch_rows + rho <= min(32 * MF_RPL, (kc.fcap - ch_off) / ch_ld);
+            if (inplace) {
+                U = ch_mask;
+            } else {
+                const int cwp = 3 * __popcll(ch_mask) + 1;
+                if (ng + 1 > ngcap || top + ch_rows * cwp > kc.acap) return 1;
+                mf_store_cb(w.front + ch_off, ch_ld, ch_rows, cwp, w.arena + top, lane);
+                if (lane == 0) {
+                    w.g_mask[ng] = ch_mask;
+                    w.g_off[ng] = top;
+                    w.g_nr[ng] = (unsigned short)ch_rows;
+                    w.g_ld[ng] = (unsigned char)cwp;
+                    if (has && nS < MF_SCAP) w.s_list[nS] = ng;
+                }
+                if (has) {
+                    nS++;
+                    U |= ch_mask;
+                    rho += ch_rows;
+                }
+                top += ch_rows * cwp;
+                ng++;
+                __syncwarp();
+            }
+        }
         const u64 Up = U & ~pbit;
         const int c = 3 * __popcll(U) + 1;
         // (c) capacity checks: group table, R slab; the front is processed in chunks of at most `rcap` rows
-        const int ld = (c + 1) & ~1;   // even row stride: rows stay 16-byte aligned for the v loads
-        const int rcap = min(32 * MF_RPL, kc.fcap / ld);
+        const int ld = inplace ? ch_ld : ((c + 1) & ~1);   // even row stride
+        const int rcap = inplace ? ch_rows + rho : min(32 * MF_RPL, kc.fcap / ld);
         const int La = c > 16 ? 32 : c > 8 ? 16 : c > 4 ? 8 : 4, Ga = 32 / La;   // assembly: lanes per front row
-        if (nS > MF_SCAP || rcap < 8 || rtop + 3 * c > kc.acap) return 1;
+        if (nS > MF_SCAP || (!inplace && rcap < 8) || rtop + 3 * c > kc.acap) return 1;
         // block id of every column slot: slot 0 = pivot, then the other blocks ascending
         if ((Up >> lane) & 1ull) w.colblk[1 + __popcll(Up & ((1ull << lane) - 1ull))] = (unsigned char)lane;
         if ((Up >> (lane + 32)) & 1ull) w.colblk[1 + __popcll(Up & ((1ull << (lane + 32)) - 1ull))] = (unsigned char)(lane + 32);
         if (lane == 0) w.colblk[0] = (unsigned char)piv;
         __syncwarp();
-        double *Fm = w.front;
+        double *Fm = inplace ? w.front + ch_off : w.front;
+        const bool par = inplace && (ch_off & 1);   // odd offset: the (v1, v2) pair is the 16-byte aligned one
         const unsigned front_s = (unsigned)__cvta_generic_to_shared(Fm);
-        const int ng0 = ng;         // groups appended below are not candidates of this elimination
         int t_next = 0, r_done = 0; // next group of the S list / rows of it already taken
-        int carry = 0;              // pivot rows of the previous chunk, kept in front rows [0, carry)
+        int carry = inplace ? ch_rows : 0;   // rows already in the front: the chained block / the previous chunk's pivot rows
+        ch_rows = 0;
         int npiv = 0;
         double fri0 = 0.0, fri1 = 0.0, fri2 = 0.0;   // 1 / alpha of the last chunk's pivots
         (void)rho;
@@ -711,7 +777,8 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
             for (int q = 0; q < MF_RPL; q++) {
                 int r = lane + 32 * q;
                 if (r < rho_c) {
-                    *reinterpret_cast<double2 *>(Fm + r * ld) = make_double2(a0[q], a1[q]);
+                    Fm[r * ld] = a0[q];
+                    Fm[r * ld + 1] = a1[q];
                     Fm[r * ld + 2] = a2[q];
                 }
             }
@@ -719,6 +786,7 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
             // (f) apply the three reflections to the other columns: two passes over the rows.  Narrow fronts
             //     (<= 16 other columns: the tall-skinny end game) split the rows over 2..32 lane groups
             const int cw3 = c - 3;
+            const int po = par ? 1 : 0, so = par ? 0 : 2;   // aligned pair of v entries / the single one
             // lanes per group: the power of two covering the columns; G = 32 / L groups take rows g, g + G, ...
             const int L = cw3 > 16 ? 32 : cw3 > 8 ? 16 : cw3 > 4 ? 8 : cw3 > 2 ? 4 : cw3 > 1 ? 2 : 1;
             if (L < 32 && cw3 > 0) {
@@ -726,33 +794,35 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
                 const bool act = jl < cw3;
                 const int j = 3 + (act ? jl : 0);
                 const int step = G * ld;
-                double w0 = 0.0, w1 = 0.0, w2 = 0.0;
+                double wa = 0.0, wb = 0.0, wc = 0.0;
                 {
                     const double *vp = Fm + grp * ld;
 #pragma unroll 4
                     for (int r = grp; r < rho_c; r += G) {
                         double f = vp[j];
-                        double2 va = *reinterpret_cast<const double2 *>(vp);
-                        double vc = vp[2];
-                        w0 += va.x * f; w1 += va.y * f; w2 += vc * f;
+                        double2 va = *reinterpret_cast<const double2 *>(vp + po);
+                        double vc = vp[so];
+                        wa += va.x * f; wb += va.y * f; wc += vc * f;
                         vp += step;
                     }
                 }
                 for (int o = L; o < 32; o <<= 1) {
-                    w0 += __shfl_xor_sync(FULL, w0, o);
-                    w1 += __shfl_xor_sync(FULL, w1, o);
-                    w2 += __shfl_xor_sync(FULL, w2, o);
+                    wa += __shfl_xor_sync(FULL, wa, o);
+                    wb += __shfl_xor_sync(FULL, wb, o);
+                    wc += __shfl_xor_sync(FULL, wc, o);
                 }
+                const double w0 = par ? wc : wa, w1 = par ? wa : wb, w2 = par ? wb : wc;
                 double s0 = beta0 * w0;
                 double s1 = beta1 * (w1 - d10 * s0);
                 double s2 = beta2 * (w2 - d20 * s0 - d21 * s1);
+                const double ca = par ? s1 : s0, cb = par ? s2 : s1, cc = par ? s0 : s2;
                 if (act) {
                     double *vp = Fm + grp * ld;
 #pragma unroll 4
                     for (int r = grp; r < rho_c; r += G) {
-                        double2 va = *reinterpret_cast<const double2 *>(vp);
-                        double vc = vp[2];
-                        vp[j] = vp[j] - (va.x * s0 + va.y * s1 + vc * s2);
+                        double2 va = *reinterpret_cast<const double2 *>(vp + po);
+                        double vc = vp[so];
+                        vp[j] = vp[j] - (va.x * ca + va.y * cb + vc * cc);
                         vp += step;
                     }
                 }
@@ -760,30 +830,32 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
             for (int j0 = 3; j0 < c; j0 += 32) {
                 int j = j0 + lane;
                 if (j >= c) continue;
-                double w0 = 0.0, w1 = 0.0, w2 = 0.0;
+                double wa = 0.0, wb = 0.0, wc = 0.0;
                 {
                     const double *fp = Fm + j;
                     const double *vp = Fm;
 #pragma unroll 4
                     for (int r = 0; r < rho_c; r++) {
                         double f = *fp;
-                        double2 va = *reinterpret_cast<const double2 *>(vp);
-                        double vc = vp[2];
-                        w0 += va.x * f; w1 += va.y * f; w2 += vc * f;
+                        double2 va = *reinterpret_cast<const double2 *>(vp + po);
+                        double vc = vp[so];
+                        wa += va.x * f; wb += va.y * f; wc += vc * f;
                         fp += ld; vp += ld;
                     }
                 }
+                const double w0 = par ? wc : wa, w1 = par ? wa : wb, w2 = par ? wb : wc;
                 double s0 = beta0 * w0;
                 double s1 = beta1 * (w1 - d10 * s0);
                 double s2 = beta2 * (w2 - d20 * s0 - d21 * s1);
+                const double ca = par ? s1 : s0, cb = par ? s2 : s1, cc = par ? s0 : s2;
                 {
                     double *fp = Fm + j;
                     const double *vp = Fm;
 #pragma unroll 4
                     for (int r = 0; r < rho_c; r++) {
-                        double2 va = *reinterpret_cast<const double2 *>(vp);
-                        double vc = vp[2];
-                        *fp = *fp - (va.x * s0 + va.y * s1 + vc * s2);
+                        double2 va = *reinterpret_cast<const double2 *>(vp + po);
+                        double vc = vp[so];
+                        *fp = *fp - (va.x * ca + va.y * cb + vc * cc);
                         fp += ld; vp += ld;
                     }
                 }
@@ -802,33 +874,15 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
             npiv = rho_c < 3 ? rho_c : 3;
             const int left = rho_c - npiv;
             const bool keep = left > 0 && Up != 0;
-            if (keep) {
+            if (keep && last) {   // stays in the front until the next pivot is known
+                ch_rows = left;
+                ch_off = (int)(Fm - w.front) + npiv * ld + 3;
+                ch_ld = ld;
+                ch_mask = Up;
+            } else if (keep) {
                 const int cw = c - 3;
                 if (ng + 1 > ngcap || top + left * cw > kc.acap) return 1;
-                if (L < 32) {   // same lane groups as the update: G rows per step
-                    const int G = 32 / L, grp = lane / L, jl = lane & (L - 1);
-                    if (jl < cw) {
-                        const double *src = Fm + (npiv + grp) * ld + 3 + jl;
-                        double *dst = w.arena + top + grp * cw + jl;
-                        for (int r = grp; r < left; r += G) {
-                            *dst = *src;
-                            src += G * ld;
-                            dst += G * cw;
-                        }
-                    }
-                } else
-                for (int j0 = 0; j0 < cw; j0 += 32) {
-                    int j = j0 + lane;
-                    if (j < cw) {
-                        const double *src = Fm + npiv * ld + 3 + j;
-                        double *dst = w.arena + top + j;
-                        for (int r = 0; r < left; r++) {
-                            *dst = *src;
-                            src += ld;
-                            dst += cw;
-                        }
-                    }
-                }
+                mf_store_cb(Fm + npiv * ld + 3, ld, left, cw, w.arena + top, lane);
                 if (lane == 0) {
                     w.g_mask[ng] = Up;
                     w.g_off[ng] = top;
@@ -842,7 +896,6 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
             __syncwarp();
         }
         for (int t = lane; t < nS; t += 32) w.g_nr[w.s_list[t] & 0xffff] = 0;   // consumed
-        (void)ng0;
         // R rows to the slab; the diagonal carries 1 / alpha so that the back substitution has no divisions
         for (int j = lane; j < c; j += 32) {
             double v0 = Fm[j], v1 = Fm[ld + j], v2 = Fm[2 * ld + j];
@@ -877,7 +930,7 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
     const double *Rbase = r_in_smem ? w.front : rslab;
     for (int i = lane; i < 3 * E; i += 32) w.gvec[i] = 0.0;
     __syncwarp();
-    for (int g = nR - 1; g >= 0; g--) {
+    for (int g = nR - 1; g >= n_leaf; g--) {
         const int meta = w.r_meta[g];
         const int piv = meta & 0xff, npiv = (meta >> 8) & 0xff, c = meta >> 16;
         const u64 Up = w.r_mask[g] & ~(1ull << piv);
@@ -910,6 +963,31 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
         }
         __syncwarp();
     }
+    // leaf fronts: their unknowns depend on non-leaf blocks only, so all of them are solved at once, one per lane
+    if (lane < n_leaf) {
+        const int meta = w.r_meta[lane];
+        const int piv = meta & 0xff, c = meta >> 16;
+        u64 Up = w.r_mask[lane] & ~(1ull << piv);
+        const double *R = Rbase + w.r_off[lane];
+        double p0 = 0.0, p1 = 0.0, p2 = 0.0;
+        for (int j = 3; Up; j += 3, Up &= Up - 1) {
+            const double *gb = w.gvec + 3 * (__ffsll((long long)Up) - 1);
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                const double gj = gb[q];
+                p0 += R[j + q] * gj;
+                p1 += R[c + j + q] * gj;
+                p2 += R[2 * c + j + q] * gj;
+            }
+        }
+        const double g2 = (R[2 * c + c - 1] - p2) * R[2 * c + 2];
+        const double g1 = (R[c + c - 1] - p1 - R[c + 2] * g2) * R[c + 1];
+        const double g0 = (R[c - 1] - p0 - R[1] * g1 - R[2] * g2) * R[0];
+        w.gvec[3 * piv] = g0;
+        w.gvec[3 * piv + 1] = g1;
+        w.gvec[3 * piv + 2] = g2;
+    }
+    __syncwarp();
     // ---- residual on the element rows, weights, CSR values ----
     double *wo = a.wbuf + ((i64)eb - a.wbase);
     double part = 0.0;
