@@ -479,13 +479,14 @@ extern "C" int npb_set_point_flags(npb_ctx *c, const int64_t *flag, int64_t n_po
         return NPB_ERR_ARG;
     }
     NPB_CUDA(cudaSetDevice(c->device));
-    i64 *tmp = nullptr;
-    NPB_CUDA(cudaMalloc(&tmp, sizeof(i64) * n_points));
+    // staged through the persistent scratch block: a cudaMalloc / cudaFree pair per call costs tens of
+    // milliseconds once gigabytes of page-locked host memory are mapped
+    NPB_TRY(npb_ensure(&c->scratch, &c->scratch_cap, sizeof(i64) * (size_t)n_points));
+    i64 *tmp = (i64 *)c->scratch;
     NPB_TRY(npb_h2d(c, tmp, flag, sizeof(i64) * n_points));
     k_flags<<<npb_blocks(n_points, 256), 256, 0, c->stream>>>(tmp, n_points, c->nflag);
     NPB_LAUNCH(c);
     NPB_CUDA(cudaStreamSynchronize(c->stream));
-    NPB_CUDA(cudaFree(tmp));
     c->have_flags = true;
     c->counted = false;
     c->fused_failed[0] = c->fused_failed[1] = false;

@@ -48,8 +48,8 @@ struct MfClass {
     int fcap_f; // max faces around the node
     int acap;   // capacity (doubles) of the CTA's global row-group arena; the R slab has the same size
 };
-#define MF_CLASS_TABLE {{0, 0, 0, 0}, {384, 8, 14, 3072}, {640, 12, 22, 6144}, {768, 16, 30, 8192}, {1408, 24, 40, 12288}, \
-                        {1536, 32, 56, 18432}, {2560, 48, 80, 32768}, {4096, 64, 112, 49152}, {0, 0, 0, 0}}
+#define MF_CLASS_TABLE {{0, 0, 0, 0}, {640, 8, 14, 3072}, {640, 12, 22, 6144}, {768, 16, 30, 8192}, {1664, 24, 40, 12288}, \
+                        {1664, 32, 56, 18432}, {2560, 48, 80, 32768}, {4096, 64, 112, 49152}, {0, 0, 0, 0}}
 __constant__ MfClass c_mf[MF_NCLASS] = MF_CLASS_TABLE;
 static MfClass h_mf[MF_NCLASS] = MF_CLASS_TABLE;
 
@@ -356,12 +356,20 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
     // ---- adjacency bitmasks: lane b owns blocks b and b + 32 ----
     u64 adjA = 0, adjB = 0;
     {
-        const u64 bitA = 1ull << lane, bitB = 1ull << (lane + 32);
-        for (int g = 0; g < ng; g++) {
-            u64 mk = w.g_mask[g];
-            if (mk & bitA) adjA |= mk;
-            if (mk & bitB) adjB |= mk;
+        u64 *adj = reinterpret_cast<u64 *>(w.gvec);   // [E], free until the back substitution
+        for (int i = lane; i < E; i += 32) adj[i] = 1ull << i;
+        __syncwarp();
+        for (int g = E + lane; g < ng; g += 32) {   // groups 0..E-1 are the element rows: one block each
+            const u64 mk = w.g_mask[g];
+            u64 m = mk;
+            atomicOr((unsigned long long *)&adj[__ffsll((long long)m) - 1], mk);
+            m &= m - 1;
+            if (m) atomicOr((unsigned long long *)&adj[__ffsll((long long)m) - 1], mk);
         }
+        __syncwarp();
+        if (lane < E) adjA = adj[lane];
+        if (lane + 32 < E) adjB = adj[lane + 32];
+        __syncwarp();
     }
     u64 alive = (E >= 64) ? ~0ull : ((1ull << E) - 1ull);
     int nR = 0, rtop = 0;   // R rows written so far (entries / doubles in the global slab)
@@ -598,17 +606,10 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
             }
             unsigned bal = __ballot_sync(FULL, in);
             if (bal == 0) continue;
-            int v = in ? nr : 0;   // exclusive prefix of the row counts over the selected lanes
-            int incl = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int t = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += t;
-            }
             int pos = nS + __popc(bal & ((1u << lane) - 1u));
-            if (in && pos < MF_SCAP) w.s_list[pos] = g | ((rho + incl - v) << 16);
+            if (in && pos < MF_SCAP) w.s_list[pos] = g;
             nS += __popc(bal);
-            rho += __shfl_sync(FULL, incl, 31);
+            rho += __reduce_add_sync(FULL, in ? nr : 0);
             U |= warp_or64(in ? mk : 0ull);
         }
         bool inplace = false;
@@ -1097,7 +1098,8 @@ int npb_k2_gls(npb_ctx *c, i64 lo, i64 hi)
         int variant = per_sm >= 16 ? 16 : 12;   // 24 (80 registers) spills the leaf fronts: only on request
         const char *var = getenv("NPB_GLS_VARIANT");
         if (var && (atoi(var) == 12 || atoi(var) == 16 || atoi(var) == 24)) variant = atoi(var);
-        if (per_sm > 65536 / (32 * (variant == 24 ? 80 : variant == 16 ? 128 : 168))) per_sm = 65536 / (32 * (variant == 24 ? 80 : variant == 16 ? 128 : 168));
+        const int vregs = variant == 24 ? 80 : variant == 16 ? 128 : 168;
+        if (per_sm > 65536 / (32 * vregs)) per_sm = 65536 / (32 * vregs);
         int grid = c->sm_count * per_sm;
         if (grid > count) grid = count;
         NPB_TRY(npb_ensure(&c->gls_ws, &c->gls_ws_cap, sizeof(double) * (size_t)grid * h_mf[k].acap * 2));

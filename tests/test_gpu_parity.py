@@ -162,6 +162,25 @@ def test_fallback_kernels_agree(kind, n, kw, monkeypatch):
             assert np.array_equal(nv, nvo)
 
 
+@pytest.mark.parametrize("kind,n,kw", [("tet", 9, {"scramble": True}), ("hex", 8, {}), ("mixed", 10, {"a": 2, "b": 5}), ("quad2d", 9, {"perturb": 0.2})])
+def test_gls_general_fronts_only(kind, n, kw, monkeypatch):
+    """NPB_GLS_NO_LEAF=1 sends every front through the general warp-per-front loop (no lane-per-leaf
+    phase): same tolerance against the oracle, and both paths agree with each other to rounding."""
+    import ninpol_b200
+    from ninpol_b200 import meshgen
+    I, O = _pair(kind, n, kw)
+    W1, nv1 = I.interpolate("u", "gls")
+    monkeypatch.setenv("NPB_GLS_NO_LEAF", "1")
+    J = ninpol_b200.Interpolator()
+    J.load_mesh(mesh_obj=meshgen.make_case(kind, n, **kw))
+    W2, nv2 = J.interpolate("u", "gls")
+    Wo, nvo = O.interpolate("u", "gls")
+    assert np.array_equal(W2.indptr, Wo.indptr) and np.array_equal(W2.indices, Wo.indices)
+    assert gls_errors(W2, Wo) <= GLS_TOL and gls_errors(W1, Wo) <= GLS_TOL
+    assert gls_errors(W1, W2) <= GLS_TOL
+    assert np.allclose(nv1, nv2, rtol=0, atol=1e-12)
+
+
 @pytest.mark.parametrize("kind,n,kw", CASES_2D)
 def test_2d_meshes_bit_exact(kind, n, kw):
     """dim == 2: faces are edges (interpolator.pyx:296-298), 2-D normal branch (grid.pyx:787-806), LS
