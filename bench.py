@@ -238,6 +238,13 @@ class Plumbing:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
+    def sum(self, v):
+        if not self.dist:
+            return float(v)
+        t = self.torch.tensor([float(v)], dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
     def close(self):
         if self.dist:
             self.dist.destroy_process_group()
@@ -286,9 +293,10 @@ def timed_e2e_steps(I, plumb, method, steps, warmup):
     I._ctx.synchronize()
     dt = time.perf_counter() - t0
     plumb.barrier()
-    g = I.grid
-    h2d = 8 * g.n_points + (8 * 10 * g.n_elems if method == "gls" else 0)
-    d2h = W.indptr.nbytes + W.indices.nbytes + W.data.nbytes + nv.nbytes
+    # bytes actually copied per step, summed over the ranks (a GLS rank uploads the slice of the cell
+    # fields its nodes read; with gather="root" only rank 0 downloads the whole CSR)
+    h2d = plumb.sum(I.last_timings["h2d_input_bytes"])
+    d2h = plumb.sum(W.indptr.nbytes + W.indices.nbytes + W.data.nbytes + nv.nbytes)
     return plumb.max(dt) / steps, int(h2d), int(d2h)
 
 
@@ -306,7 +314,7 @@ def run_ours(args, rank, world):
     if rank == 0:
         log(f"mesh {desc}: generated in {time.time() - t0:.1f}s")
     t0 = time.time()
-    I = ninpol_b200.Interpolator(comm=comm, pinned_outputs=True, pin_inputs=True)
+    I = ninpol_b200.Interpolator(comm=comm, pinned_outputs=True, pin_inputs=True, gather="root")
     I.load_mesh(mesh_obj=mesh)
     t_load = time.time() - t0
     ctx = I._ctx
@@ -318,7 +326,7 @@ def run_ours(args, rank, world):
             f"faces {k1['k1_faces']:.1f}, fsup {k1['k1_fsup']:.1f}, geom {k1['k1_geom']:.1f}); H2D {k1['h2d_mesh']:.1f} ms")
     method = args.method
     W0, _ = I.interpolate(VARIABLE, method)      # stages the inputs, sets the partition
-    nnz = W0.nnz
+    nnz = int(np.asarray(g.esup_ptr)[-1]) if world > 1 and rank != 0 else W0.nnz   # only rank 0 prints it
     del W0
     sampler = ClockSampler(ctx.device) if rank == 0 else None
     ms_step, k2_ms, main_ms, launches, clocks = timed_device_steps(I, plumb, method, args.steps, max(args.warmup, 3), sampler)
@@ -339,16 +347,17 @@ def run_ours(args, rank, world):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc, "method": method, "n_nodes": n_points, "n_cells": n_elems, "nnz": nnz,
-                   "processed_nodes": n_proc, "partition": f"nodes split into {world} contiguous cost-balanced ranges; mesh replicated",
+                   "processed_nodes": n_proc, "partition": f"nodes split into {world} contiguous cost-balanced ranges; mesh replicated; row blocks gathered to rank 0",
                    "cache": "inputs larger than L2 (working set >> 126 MB); no flush needed" if n_elems > 2_000_000 else
                             "small workload: L2-resident between iterations"},
         "e2e": {"value": n_points / e2e_s, "unit": "nodes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_s * 1e3, "api": "Interpolator(pinned_outputs=True, pin_inputs=True).interpolate(variable, method) after invalidate_inputs(): "
-                "H2D of flags (+permeability, diff_mag) from page-locked host arrays + K2 + K3 (+K4) + D2H of the CSR into "
-                "page-locked numpy buffers, scipy.csr_matrix wrap"},
+                "ms_per_step": e2e_s * 1e3, "api": "Interpolator(pinned_outputs=True, pin_inputs=True, gather='root').interpolate(variable, method) after "
+                "invalidate_inputs(): H2D of flags (+ the slice of permeability / diff_mag this rank's nodes read) from page-locked "
+                "host arrays + K2 + K3 (+ K4: row blocks to rank 0 over NCCL) + D2H of the CSR (rank 0: all of it; other ranks: "
+                "their own rows) into page-locked numpy buffers, scipy.csr_matrix wrap; byte counts are sums over ranks"},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_gls_nodes (largest size class)" if method == "gls" else f"k_{method}",
+        "roofline": {"bound": "hbm", "kernel": "k_gls_mf (largest size class)" if method == "gls" else f"k_{method}",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": profiled_traffic(args.workload, method), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": nbytes * share, "kernel_ms": kern_ms, "k2_ms": k2_ms},

@@ -1,9 +1,3 @@
-python tools/stage_probe.py 100 2>&1 | grep -A2 "rep 2" 
-echo "== hex v16"; python tools/run_once.py hex 128 gls 2 2>&1 | tail -1 | cut -c1-100
-echo "== hex v20"; NPB_GLS_VARIANT=20 python tools/run_once.py hex 128 gls 2 2>&1 | tail -1 | cut -c1-100
-python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; tail -1 gpurun_out/bench_c4.err
-python - <<'PY'
-import json
-d=json.load(open("gpurun_out/bench_c4.json"))
-print({k:d[k] for k in ("metric","value","ms_per_step","gpu_launches")}, d["e2e"]["value"], d["e2e"]["ms_per_step"])
-PY
+python tools/run_once.py tet 203 gls > gpurun_out/plain_c4.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:k_gls_mf -s 2 -c 1 -o gpurun_out/prof_gls_c4_v2 python tools/run_once.py tet 203 gls > gpurun_out/ncu_c4.log 2>&1
+tail -1 gpurun_out/plain_c4.log | cut -c1-200; tail -2 gpurun_out/ncu_c4.log

@@ -58,6 +58,16 @@ int npb_comm_init(npb_ctx *ctx, const void *id, int rank, int world);
 /* node ranges of all ranks: bounds[world+1], bounds[0]=0, bounds[world]=n_points, non-decreasing.
  * Default (never called, or world==1): this rank owns every node. */
 int npb_set_partition(npb_ctx *ctx, const int64_t *bounds, int n_bounds);
+/* Who receives the assembled CSR when world > 1: NPB_GATHER_ALL (default) all-gathers the row blocks to
+ * every rank; NPB_GATHER_ROOT sends them to rank 0 only - the other ranks' npb_interpolate_count /
+ * npb_interpolate_fetch then return their own row block (rows of other ranks empty, shape unchanged). */
+#define NPB_GATHER_ALL 0
+#define NPB_GATHER_ROOT 1
+int npb_set_gather(npb_ctx *ctx, int mode);
+/* Closed range [first, last] of the element ids that occur in the node->element rows of this rank's node
+ * range (after npb_set_partition): the only elements whose cell fields the rank's nodes read, so a rank
+ * needs to upload just that slice (npb_set_cell_field_range).  first > last for an empty node range. */
+int npb_partition_elem_range(npb_ctx *ctx, int64_t *first, int64_t *last);
 
 /* K1 — connectivity + geometry on the device.
  * Replaces: Grid.__cinit__ + Grid.build + load_point_coords + calculate_centroids +
@@ -88,6 +98,11 @@ int npb_grid_array(npb_ctx *ctx, const char *name, void *out, int64_t capacity_b
  * per element) or "diff_mag" (n = n_elems).  neumann_flag holds int64 truncations of the point data
  * (non-zero = Neumann node), exactly what `.astype(int)` yields in the reference. */
 int npb_set_cell_field(npb_ctx *ctx, const char *name, const double *data, int64_t n);
+/* Same, for the elements [first_elem, first_elem + n_elems_in_range) only: data holds 9 (permeability) or
+ * 1 (diff_mag) values per element of the range.  Values of elements outside every uploaded range are
+ * unspecified; a rank needs the range npb_partition_elem_range reports. */
+int npb_set_cell_field_range(npb_ctx *ctx, const char *name, const double *data, int64_t first_elem,
+                             int64_t n_elems_in_range);
 int npb_set_point_flags(npb_ctx *ctx, const int64_t *neumann_flag, int64_t n_points);
 
 /* K2 + K3 (+ K4) — weights and CSR.

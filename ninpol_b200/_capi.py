@@ -24,6 +24,9 @@ _SIGNATURES = {
     "npb_comm_unique_id": (ctypes.c_int, [ctypes.c_void_p]),
     "npb_comm_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
     "npb_set_partition": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "npb_set_gather": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "npb_partition_elem_range": (ctypes.c_int, [ctypes.c_void_p, _c_i64p, _c_i64p]),
+    "npb_set_cell_field_range": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64]),
     "npb_load_mesh": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64] + [ctypes.c_void_p] * 9 + [ctypes.c_int]),
     "npb_grid_scalar": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, _c_i64p]),
     "npb_grid_array": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64]),
@@ -122,6 +125,16 @@ class Context:
         b = np.ascontiguousarray(bounds, dtype=np.int64)
         check(self.lib.npb_set_partition(self.handle, _ptr(b), len(b)))
 
+    def set_gather(self, mode):
+        """'all': every rank receives the full CSR; 'root': rank 0 only, the others keep their row block."""
+        check(self.lib.npb_set_gather(self.handle, {"all": 0, "root": 1}[mode]))
+
+    def partition_elem_range(self):
+        """Closed range of the element ids this rank's nodes touch (first > last when it owns no node)."""
+        a, b = ctypes.c_int64(0), ctypes.c_int64(-1)
+        check(self.lib.npb_partition_elem_range(self.handle, ctypes.byref(a), ctypes.byref(b)))
+        return int(a.value), int(b.value)
+
     # --- K1 ---
     def load_mesh(self, dim, n_elems, n_points, conn, etype, npoel, nfael, lnofa, lpofa, nedel, lpoed, coords, build_edges):
         arrs = [np.ascontiguousarray(a, dtype=np.int64) for a in (conn, etype, npoel, nfael, lnofa, lpofa, nedel, lpoed)]
@@ -144,6 +157,13 @@ class Context:
     def set_cell_field(self, name, data):
         d = np.ascontiguousarray(data, dtype=np.float64).ravel()
         check(self.lib.npb_set_cell_field(self.handle, name.encode(), _ptr(d), d.size))
+
+    def set_cell_field_range(self, name, data, first_elem, count):
+        """`data` = the slice of the field that belongs to elements [first_elem, first_elem + count)."""
+        d = np.ascontiguousarray(data, dtype=np.float64).ravel()
+        per = 9 if name == "permeability" else 1
+        assert d.size == per * count, (d.size, per, count)
+        check(self.lib.npb_set_cell_field_range(self.handle, name.encode(), _ptr(d), int(first_elem), int(count)))
 
     def set_point_flags(self, flags):
         f = np.ascontiguousarray(flags, dtype=np.int64)

@@ -295,6 +295,36 @@ extern "C" int npb_set_partition(npb_ctx *c, const int64_t *bounds, int n_bounds
     return refresh_range(c);
 }
 
+extern "C" int npb_set_gather(npb_ctx *c, int mode)
+{
+    if (!c || (mode != NPB_GATHER_ALL && mode != NPB_GATHER_ROOT)) {
+        npb_set_error("npb_set_gather: mode must be NPB_GATHER_ALL or NPB_GATHER_ROOT");
+        return NPB_ERR_ARG;
+    }
+    c->gather_mode = mode;
+    c->counted = false;
+    return NPB_OK;
+}
+
+extern "C" int npb_partition_elem_range(npb_ctx *c, int64_t *first, int64_t *last)
+{
+    if (!c || !first || !last) return NPB_ERR_ARG;
+    if (!c->mesh_loaded) {
+        npb_set_error("npb_partition_elem_range: no mesh loaded");
+        return NPB_ERR_STATE;
+    }
+    NPB_CUDA(cudaSetDevice(c->device));
+    int32_t ptr[2] = {0, 0};
+    NPB_CUDA(cudaMemcpyAsync(&ptr[0], c->esup_ptr + c->lo, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    NPB_CUDA(cudaMemcpyAsync(&ptr[1], c->esup_ptr + c->hi, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    NPB_CUDA(cudaStreamSynchronize(c->stream));
+    int32_t mn = 0, mx = -1;
+    NPB_TRY(npb_minmax_i32(c, c->esup + ptr[0], (i64)ptr[1] - ptr[0], &mn, &mx));
+    *first = mn;
+    *last = mx;
+    return NPB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1
 // ------------------------------------------------------------------------------------------------
@@ -461,6 +491,37 @@ extern "C" int npb_set_cell_field(npb_ctx *c, const char *name, const double *da
     return NPB_OK;
 }
 
+extern "C" int npb_set_cell_field_range(npb_ctx *c, const char *name, const double *data, int64_t first_elem,
+                                        int64_t n_elems_in_range)
+{
+    if (!c || !name || (!data && n_elems_in_range > 0)) return NPB_ERR_ARG;
+    if (!c->mesh_loaded) {
+        npb_set_error("npb_set_cell_field_range: no mesh loaded");
+        return NPB_ERR_STATE;
+    }
+    if (first_elem < 0 || n_elems_in_range < 0 || first_elem + n_elems_in_range > c->n_elems) {
+        npb_set_error("npb_set_cell_field_range: elements [%lld, %lld) outside [0, %lld)", (long long)first_elem,
+                      (long long)(first_elem + n_elems_in_range), (long long)c->n_elems);
+        return NPB_ERR_ARG;
+    }
+    NPB_CUDA(cudaSetDevice(c->device));
+    if (strcmp(name, "permeability") == 0) {
+        if (!c->perm) NPB_TRY(npb_alloc(c, (void **)&c->perm, sizeof(double) * 9 * (size_t)c->n_elems));
+        NPB_TRY(npb_h2d(c, c->perm + 9 * first_elem, data, sizeof(double) * 9 * (size_t)n_elems_in_range));
+        c->have_perm = true;
+    } else if (strcmp(name, "diff_mag") == 0) {
+        if (!c->diff_mag) NPB_TRY(npb_alloc(c, (void **)&c->diff_mag, sizeof(double) * (size_t)c->n_elems));
+        NPB_TRY(npb_h2d(c, c->diff_mag + first_elem, data, sizeof(double) * (size_t)n_elems_in_range));
+        c->have_dm = true;
+    } else {
+        npb_set_error("npb_set_cell_field_range: unknown field '%s'", name);
+        return NPB_ERR_ARG;
+    }
+    NPB_CUDA(cudaStreamSynchronize(c->stream));
+    c->counted = false;
+    return NPB_OK;
+}
+
 __global__ void k_flags(const i64 *__restrict__ in, i64 n, uint8_t *__restrict__ out)
 {
     i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -531,6 +592,8 @@ extern "C" int npb_interpolate_count(npb_ctx *c, int method, int64_t *nnz)
             c->method = method;
             c->counted = true;
             c->filled = true;
+            c->nnz_ret = c->nnz;
+            c->blk_off = 0;
             *nnz = c->nnz;
             return NPB_OK;
         }
@@ -565,9 +628,19 @@ extern "C" int npb_interpolate_count(npb_ctx *c, int method, int64_t *nnz)
         tm.stop();
         c->nnz = total;
     }
+    c->nnz_ret = c->nnz;
+    c->blk_off = 0;
+    if (c->world > 1 && c->gather_mode == NPB_GATHER_ROOT && c->rank != 0) {
+        int32_t o[2] = {0, 0};
+        NPB_CUDA(cudaMemcpyAsync(&o[0], c->indptr + c->lo, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        NPB_CUDA(cudaMemcpyAsync(&o[1], c->indptr + c->hi, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        NPB_CUDA(cudaStreamSynchronize(s));
+        c->blk_off = o[0];
+        c->nnz_ret = (i64)o[1] - o[0];
+    }
     c->method = method;
     c->counted = true;
-    *nnz = c->nnz;
+    *nnz = c->nnz_ret;
     return NPB_OK;
 }
 
@@ -585,6 +658,15 @@ int npb_ensure_out(npb_ctx *c, size_t n)
     NPB_CUDA(cudaMalloc(&c->data, sizeof(double) * want));
     c->out_cap = want;
     return NPB_OK;
+}
+
+__global__ void k_block_indptr(const int32_t *__restrict__ indptr, i64 n, int32_t lo, int32_t hi, int32_t *__restrict__ out)
+{
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        int32_t v = indptr[i];
+        out[i] = (v < lo ? lo : v > hi ? hi : v) - lo;
+    }
 }
 
 extern "C" int npb_interpolate_fetch(npb_ctx *c, int32_t *indptr, int32_t *indices, double *data, double *neumann)
@@ -610,9 +692,19 @@ extern "C" int npb_interpolate_fetch(npb_ctx *c, int32_t *indptr, int32_t *indic
     }
     {
         NpbTimer tm(c, "d2h_csr");
-        if (indptr) NPB_TRY(npb_d2h(c, indptr, c->indptr, sizeof(int32_t) * (c->n_points + 1)));
-        if (indices && c->nnz > 0) NPB_TRY(npb_d2h(c, indices, c->indices, sizeof(int32_t) * c->nnz));
-        if (data && c->nnz > 0) NPB_TRY(npb_d2h(c, data, c->data, sizeof(double) * c->nnz));
+        const bool block_only = c->world > 1 && c->gather_mode == NPB_GATHER_ROOT && c->rank != 0;
+        if (indptr && block_only) {
+            // this rank's rows only: indptr clamped to the block and rebased, rows of other ranks empty
+            NPB_TRY(npb_ensure(&c->scratch, &c->scratch_cap, sizeof(int32_t) * (size_t)(c->n_points + 1)));
+            k_block_indptr<<<npb_blocks(c->n_points + 1, 256), 256, 0, s>>>(c->indptr, c->n_points + 1, (int32_t)c->blk_off,
+                                                                           (int32_t)(c->blk_off + c->nnz_ret),
+                                                                           (int32_t *)c->scratch);
+            NPB_LAUNCH(c);
+            NPB_TRY(npb_d2h(c, indptr, c->scratch, sizeof(int32_t) * (c->n_points + 1)));
+        } else if (indptr)
+            NPB_TRY(npb_d2h(c, indptr, c->indptr, sizeof(int32_t) * (c->n_points + 1)));
+        if (indices && c->nnz_ret > 0) NPB_TRY(npb_d2h(c, indices, c->indices + c->blk_off, sizeof(int32_t) * c->nnz_ret));
+        if (data && c->nnz_ret > 0) NPB_TRY(npb_d2h(c, data, c->data + c->blk_off, sizeof(double) * c->nnz_ret));
         if (neumann) NPB_TRY(npb_d2h(c, neumann, c->neumann, sizeof(double) * c->n_points));
         tm.stop();
     }

@@ -101,6 +101,8 @@ struct npb_ctx {
     bool fused_failed[2] = {false, false};   // per method: the single-pass emit met an exact zero for the current inputs
     bool filled = false;         // indices / data already hold the CSR (fused path, or k3_fill done)
     i64 nnz = 0;
+    i64 nnz_ret = 0, blk_off = 0;   // what count / fetch hand out: all of it, or this rank's row block (gather to root)
+    int gather_mode = 0;            // NPB_GATHER_ALL / NPB_GATHER_ROOT
     double *wbuf = nullptr;      // final data values, esup-indexed, local node range
     size_t wbuf_cap = 0;
     int32_t *rowcnt = nullptr;   // [n_points + 1]
@@ -151,6 +153,7 @@ int npb_k2_idw_ls_tiles(npb_ctx *c, int method, i64 lo, i64 hi, int *used);
 int npb_ensure_out(npb_ctx *c, size_t n);
 int npb_k2_gls(npb_ctx *c, i64 lo, i64 hi);
 int npb_k3_fill(npb_ctx *c, i64 lo, i64 hi);
+int npb_minmax_i32(npb_ctx *c, const int32_t *in, i64 n, int32_t *h_min, int32_t *h_max);
 int npb_k4_gather_counts(npb_ctx *c);
 int npb_k4_gather_blocks(npb_ctx *c);
 int npb_export_array(npb_ctx *c, const char *name, void *out, i64 cap);

@@ -18,6 +18,8 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -48,6 +50,8 @@ static int load_nccl()
     SYM(CommInitRank, "ncclCommInitRank")
     SYM(CommDestroy, "ncclCommDestroy")
     SYM(Broadcast, "ncclBroadcast")
+    SYM(Send, "ncclSend")
+    SYM(Recv, "ncclRecv")
     SYM(GroupStart, "ncclGroupStart")
     SYM(GroupEnd, "ncclGroupEnd")
     SYM(GetErrorString, "ncclGetErrorString")
@@ -138,11 +142,26 @@ int npb_k4_gather_blocks(npb_ctx *c)
         NPB_CUDA(cudaMemcpyAsync(&off[r], c->indptr + c->bounds[r], sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     NPB_CUDA(cudaStreamSynchronize(c->stream));
     NPB_NCCL(api->GroupStart());
-    for (int r = 0; r < c->world; r++) {
-        i64 b = off[r], n = (i64)off[r + 1] - off[r];
-        if (n <= 0) continue;
-        NPB_NCCL(api->Broadcast(c->indices + b, c->indices + b, (size_t)n, ncclInt32, r, comm, c->stream));
-        NPB_NCCL(api->Broadcast(c->data + b, c->data + b, (size_t)n, ncclFloat64, r, comm, c->stream));
+    if (c->gather_mode == NPB_GATHER_ROOT) {
+        // gather-v to rank 0: the other ranks keep (and later hand out) their own row block only
+        for (int r = 1; r < c->world; r++) {
+            i64 b = off[r], n = (i64)off[r + 1] - off[r];
+            if (n <= 0) continue;
+            if (c->rank == 0) {
+                NPB_NCCL(api->Recv(c->indices + b, (size_t)n, ncclInt32, r, comm, c->stream));
+                NPB_NCCL(api->Recv(c->data + b, (size_t)n, ncclFloat64, r, comm, c->stream));
+            } else if (c->rank == r) {
+                NPB_NCCL(api->Send(c->indices + b, (size_t)n, ncclInt32, 0, comm, c->stream));
+                NPB_NCCL(api->Send(c->data + b, (size_t)n, ncclFloat64, 0, comm, c->stream));
+            }
+        }
+    } else {
+        for (int r = 0; r < c->world; r++) {
+            i64 b = off[r], n = (i64)off[r + 1] - off[r];
+            if (n <= 0) continue;
+            NPB_NCCL(api->Broadcast(c->indices + b, c->indices + b, (size_t)n, ncclInt32, r, comm, c->stream));
+            NPB_NCCL(api->Broadcast(c->data + b, c->data + b, (size_t)n, ncclFloat64, r, comm, c->stream));
+        }
     }
     NPB_NCCL(api->GroupEnd());
     return NPB_OK;

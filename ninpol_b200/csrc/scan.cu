@@ -38,6 +38,28 @@ int npb_max_i32(npb_ctx *c, const int32_t *in, i64 n, int32_t *host_out)
     return NPB_OK;
 }
 
+int npb_minmax_i32(npb_ctx *c, const int32_t *in, i64 n, int32_t *h_min, int32_t *h_max)
+{
+    *h_min = 0;
+    *h_max = -1;
+    if (n <= 0) return NPB_OK;
+    size_t need = 0, need2 = 0;
+    int32_t *d_out = (int32_t *)(c->counters + 16);
+    NPB_CUDA(cub::DeviceReduce::Max(nullptr, need, in, d_out, (int)n, c->stream));
+    NPB_CUDA(cub::DeviceReduce::Min(nullptr, need2, in, d_out + 1, (int)n, c->stream));
+    if (need2 > need) need = need2;
+    NPB_TRY(npb_ensure(&c->scratch, &c->scratch_cap, need));
+    NPB_CUDA(cub::DeviceReduce::Max(c->scratch, need, in, d_out, (int)n, c->stream));
+    NPB_CUDA(cub::DeviceReduce::Min(c->scratch, need, in, d_out + 1, (int)n, c->stream));
+    c->launches += 4;
+    int32_t h[2];
+    NPB_CUDA(cudaMemcpyAsync(h, d_out, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    NPB_CUDA(cudaStreamSynchronize(c->stream));
+    *h_max = h[0];
+    *h_min = h[1];
+    return NPB_OK;
+}
+
 struct ClassIs {
     const uint8_t *cls;
     int which;

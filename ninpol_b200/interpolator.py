@@ -73,7 +73,7 @@ class _Method:
 
 class Interpolator:
     def __init__(self, name="interpolator", logging=False, build_edges=False, device=None, comm=None,
-                 pinned_outputs=False, pin_inputs=False):
+                 pinned_outputs=False, pin_inputs=False, gather="all"):
         # pinned_outputs=True: the CSR / neumann arrays returned by interpolate() live in page-locked
         # buffers that are REUSED by the next interpolate() call (faster device->host copies)
         self.pinned_outputs = pinned_outputs
@@ -111,8 +111,14 @@ class Interpolator:
         if device is None:
             device = self.comm.local_rank if self.comm.world > 1 else 0
         self._ctx = _capi.Context(device)      # raises when the library or the GPU is missing
+        # gather="all": every rank returns the full CSR; gather="root": rank 0 does, the other ranks
+        # return the rows they own (other rows empty) and the blocks travel to rank 0 only
+        if gather not in ("all", "root"):
+            raise ValueError("gather must be 'all' or 'root'")
+        self.gather = gather
         if self.comm.world > 1:
             self._ctx.comm_init(self.comm.unique_id, self.comm.rank, self.comm.world)
+            self._ctx.set_gather(gather)
         self._staged = None
         self._partition_key = None
         self.last_timings = {}
@@ -368,13 +374,26 @@ class Interpolator:
             return
         flags = np.asarray(points_data[flag_index])[:g.n_points].astype(DTYPE_I)
         self._ctx.set_point_flags(flags)
+        self._flags_host = flags
+        self._staged = key
+        h2d = flags.nbytes
+        self._set_partition(method)        # the node ranges depend on the flags (skipped nodes cost nothing)
         if method == "gls":
             perm = np.ascontiguousarray(np.asarray(cells_data[permeability_index])[:g.n_elems * 9], dtype=DTYPE_F)
             dm = np.ascontiguousarray(np.asarray(cells_data[diff_mag_index])[:g.n_elems], dtype=DTYPE_F)
-            self._ctx.set_cell_field("permeability", self._maybe_pin("permeability", perm))
-            self._ctx.set_cell_field("diff_mag", self._maybe_pin("diff_mag", dm))
-        self._flags_host = flags
-        self._staged = key
+            perm, dm = self._maybe_pin("permeability", perm), self._maybe_pin("diff_mag", dm)
+            if self.comm.world > 1:
+                # a rank's nodes read the cell fields of the elements in their own esup rows only
+                first, last = self._ctx.partition_elem_range()
+                cnt = max(0, last - first + 1)
+                self._ctx.set_cell_field_range("permeability", perm[9 * first:9 * (first + cnt)], first, cnt)
+                self._ctx.set_cell_field_range("diff_mag", dm[first:first + cnt], first, cnt)
+                h2d += 80 * cnt
+            else:
+                self._ctx.set_cell_field("permeability", perm)
+                self._ctx.set_cell_field("diff_mag", dm)
+                h2d += perm.nbytes + dm.nbytes
+        self.last_timings["h2d_input_bytes"] = h2d
 
     def _maybe_pin(self, name, arr):
         if not self.pin_inputs or arr.nbytes < (8 << 20):
@@ -388,6 +407,14 @@ class Interpolator:
             except _capi.NinpolB200Error:
                 self._registered.pop(name, None)     # not registrable (e.g. read-only mapping): staged copy
         return arr
+
+    def set_gather(self, gather):
+        """Switch between gather="all" and gather="root" on a live communicator (see __init__)."""
+        if gather not in ("all", "root"):
+            raise ValueError("gather must be 'all' or 'root'")
+        self.gather = gather
+        if self.comm.world > 1:
+            self._ctx.set_gather(gather)
 
     def invalidate_inputs(self):
         """Forget which per-variable inputs are resident on the device: the next interpolate() uploads
