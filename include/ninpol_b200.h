@@ -104,6 +104,9 @@ int npb_set_cell_field(npb_ctx *ctx, const char *name, const double *data, int64
 int npb_set_cell_field_range(npb_ctx *ctx, const char *name, const double *data, int64_t first_elem,
                              int64_t n_elems_in_range);
 int npb_set_point_flags(npb_ctx *ctx, const int64_t *neumann_flag, int64_t n_points);
+/* Same, from the float64 point-data row itself: the `.astype(int)` truncation (NaN / inf -> non-zero, as
+ * numpy casts them) happens on the device, which saves the host a pass over the array. */
+int npb_set_point_flags_f64(npb_ctx *ctx, const double *neumann_flag, int64_t n_points);
 
 /* K2 + K3 (+ K4) — weights and CSR.
  * Replaces: Interpolator.prepare_interpolator -> XInterpolation.prepare (interpolator.pyx:631-670;
@@ -117,6 +120,18 @@ int npb_set_point_flags(npb_ctx *ctx, const int64_t *neumann_flag, int64_t n_poi
  * Any output pointer may be NULL to skip that copy. */
 int npb_interpolate_count(npb_ctx *ctx, int method, int64_t *nnz);
 int npb_interpolate_fetch(npb_ctx *ctx, int32_t *indptr, int32_t *indices, double *data, double *neumann);
+
+/* The same result as npb_interpolate_count + npb_interpolate_fetch, computed as a pipeline over n_chunks
+ * contiguous node chunks on one GPU: the cell-field slice of chunk k+1 is uploaded and the CSR block of
+ * chunk k-1 is downloaded while chunk k computes (three CUDA streams).  perm_host / diff_mag_host: the
+ * full host arrays (9*n_elems / n_elems doubles) to upload slice by slice for GLS, or NULL to use the
+ * fields already set with npb_set_cell_field.  indices / data must hold `capacity` entries, with
+ * capacity >= the number of node->element incidences (grid scalar "len_esup"), the upper bound of nnz;
+ * indptr n_points+1, neumann n_points.  All host arrays must be page-locked.  No reference counterpart
+ * (host orchestration of interpolator.pyx:579-624 for a device that sits behind PCIe). */
+int npb_interpolate_streamed(npb_ctx *ctx, int method, int n_chunks, const double *perm_host,
+                             const double *diff_mag_host, int32_t *indptr, int32_t *indices, double *data,
+                             double *neumann, int64_t capacity, int64_t *nnz);
 
 /* Device-side timings (CUDA events on the context's stream) of the most recent calls, in ms.
  * Names: "k1" "k1_esup" "k1_esuel" "k1_faces" "k1_fsup" "k1_geom" "k2" "k3_count" "k3_fill" "k4_gather"

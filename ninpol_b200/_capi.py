@@ -32,8 +32,10 @@ _SIGNATURES = {
     "npb_grid_array": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64]),
     "npb_set_cell_field": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64]),
     "npb_set_point_flags": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]),
+    "npb_set_point_flags_f64": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]),
     "npb_interpolate_count": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_i64p]),
     "npb_interpolate_fetch": (ctypes.c_int, [ctypes.c_void_p] * 5),
+    "npb_interpolate_streamed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 6 + [ctypes.c_int64, _c_i64p]),
     "npb_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]),
     "npb_launch_count": (ctypes.c_int, [ctypes.c_void_p, _c_i64p]),
     "npb_measure_fp64_peak": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),
@@ -166,10 +168,25 @@ class Context:
         check(self.lib.npb_set_cell_field_range(self.handle, name.encode(), _ptr(d), int(first_elem), int(count)))
 
     def set_point_flags(self, flags):
+        """int64 flags, or the float64 point-data row as it is (truncated on the device like `.astype(int)`)."""
+        flags = np.asarray(flags)
+        if flags.dtype == np.float64 and flags.flags.c_contiguous:
+            check(self.lib.npb_set_point_flags_f64(self.handle, _ptr(flags), flags.size))
+            return
         f = np.ascontiguousarray(flags, dtype=np.int64)
         check(self.lib.npb_set_point_flags(self.handle, _ptr(f), f.size))
 
     # --- K2 / K3 / K4 ---
+    def interpolate_streamed(self, method, n_chunks, perm, diff_mag, indptr, indices, data, neumann):
+        """Pipelined count + fetch (stream.cu); all arrays page-locked, indices / data sized for len_esup."""
+        nnz = ctypes.c_int64(0)
+        check(self.lib.npb_interpolate_streamed(self.handle, METHOD_IDS[method], int(n_chunks),
+                                                _ptr(perm) if perm is not None else None,
+                                                _ptr(diff_mag) if diff_mag is not None else None,
+                                                _ptr(indptr), _ptr(indices), _ptr(data), _ptr(neumann),
+                                                int(min(indices.size, data.size)), ctypes.byref(nnz)))
+        return int(nnz.value)
+
     def interpolate_count(self, method):
         nnz = ctypes.c_int64(0)
         check(self.lib.npb_interpolate_count(self.handle, METHOD_IDS[method], ctypes.byref(nnz)))

@@ -49,6 +49,17 @@ int npb_ensure(void **p, size_t *cap, size_t bytes)
     return NPB_OK;
 }
 
+__global__ void k_copy_int(int *dst, const int *src) { *dst = *src; }
+
+int npb_read_int(npb_ctx *c, const int *d_src, int *h_out)
+{
+    k_copy_int<<<1, 1, 0, c->stream>>>(c->d_small + 8, d_src);
+    NPB_LAUNCH(c);
+    NPB_CUDA(cudaStreamSynchronize(c->stream));
+    *h_out = c->h_small[8];
+    return NPB_OK;
+}
+
 NpbTimer::NpbTimer(npb_ctx *c_, const char *n, bool accumulate_) : c(c_), name(n), a(nullptr), b(nullptr), accumulate(accumulate_)
 {
     cudaEventCreate(&a);
@@ -100,7 +111,7 @@ static void par_memcpy(void *dst, const void *src, size_t n)
     for (int t = 0; t < NPB_STAGE_THREADS; t++) th[t].join();
 }
 
-static bool is_pinned(const void *p)
+bool npb_is_pinned(const void *p)
 {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
@@ -123,7 +134,7 @@ static int ensure_stage(npb_ctx *c)
 int npb_h2d(npb_ctx *c, void *dst_dev, const void *src_host, size_t bytes)
 {
     if (bytes == 0) return NPB_OK;
-    if (bytes < ((size_t)8 << 20) || is_pinned(src_host)) {
+    if (bytes < ((size_t)8 << 20) || npb_is_pinned(src_host)) {
         NPB_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, c->stream));
         return NPB_OK;
     }
@@ -143,7 +154,7 @@ int npb_h2d(npb_ctx *c, void *dst_dev, const void *src_host, size_t bytes)
 int npb_d2h(npb_ctx *c, void *dst_host, const void *src_dev, size_t bytes)
 {
     if (bytes == 0) return NPB_OK;
-    if (bytes < ((size_t)8 << 20) || is_pinned(dst_host)) {
+    if (bytes < ((size_t)8 << 20) || npb_is_pinned(dst_host)) {
         NPB_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, c->stream));
         NPB_CUDA(cudaStreamSynchronize(c->stream));
         return NPB_OK;
@@ -217,6 +228,8 @@ extern "C" int npb_create(int device, npb_ctx **out)
     NPB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     NPB_CUDA(cudaMalloc(&c->counters, sizeof(int) * 64));
     NPB_CUDA(cudaMemset(c->counters, 0, sizeof(int) * 64));
+    NPB_CUDA(cudaHostAlloc((void **)&c->h_small, sizeof(int) * 64, cudaHostAllocMapped));
+    NPB_CUDA(cudaHostGetDevicePointer((void **)&c->d_small, c->h_small, 0));
     *out = c;
     return NPB_OK;
 }
@@ -234,10 +247,14 @@ extern "C" int npb_destroy(npb_ctx *c)
     if (c->scratch) cudaFree(c->scratch);
     if (c->gls_ws) cudaFree(c->gls_ws);
     if (c->counters) cudaFree(c->counters);
+    if (c->h_small) cudaFreeHost(c->h_small);
     for (int i = 0; i < 2; i++) {
         if (c->stage[i]) cudaFreeHost(c->stage[i]);
         if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
     }
+    for (cudaEvent_t e : c->pipe_ev) cudaEventDestroy(e);
+    if (c->up_stream) cudaStreamDestroy(c->up_stream);
+    if (c->down_stream) cudaStreamDestroy(c->down_stream);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_b) cudaEventDestroy(c->ev_b);
     cudaStreamDestroy(c->stream);
@@ -546,6 +563,39 @@ extern "C" int npb_set_point_flags(npb_ctx *c, const int64_t *flag, int64_t n_po
     i64 *tmp = (i64 *)c->scratch;
     NPB_TRY(npb_h2d(c, tmp, flag, sizeof(i64) * n_points));
     k_flags<<<npb_blocks(n_points, 256), 256, 0, c->stream>>>(tmp, n_points, c->nflag);
+    NPB_LAUNCH(c);
+    NPB_CUDA(cudaStreamSynchronize(c->stream));
+    c->have_flags = true;
+    c->counted = false;
+    c->fused_failed[0] = c->fused_failed[1] = false;
+    return NPB_OK;
+}
+
+__global__ void k_flags_f64(const double *__restrict__ in, i64 n, uint8_t *__restrict__ out)
+{
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        double f = in[i];
+        // numpy's float64 -> int64 cast truncates toward zero; NaN / inf become INT64_MIN (non-zero)
+        out[i] = (f != f || (long long)f != 0) ? 1 : 0;
+    }
+}
+
+extern "C" int npb_set_point_flags_f64(npb_ctx *c, const double *flag, int64_t n_points)
+{
+    if (!c || !flag) return NPB_ERR_ARG;
+    if (!c->mesh_loaded) {
+        npb_set_error("npb_set_point_flags_f64: no mesh loaded");
+        return NPB_ERR_STATE;
+    }
+    if (n_points != c->n_points) {
+        npb_set_error("neumann flags need n_points = %lld values, got %lld", (long long)c->n_points, (long long)n_points);
+        return NPB_ERR_ARG;
+    }
+    NPB_CUDA(cudaSetDevice(c->device));
+    NPB_TRY(npb_ensure(&c->scratch, &c->scratch_cap, sizeof(double) * (size_t)n_points));
+    NPB_TRY(npb_h2d(c, c->scratch, flag, sizeof(double) * n_points));
+    k_flags_f64<<<npb_blocks(n_points, 256), 256, 0, c->stream>>>((const double *)c->scratch, n_points, c->nflag);
     NPB_LAUNCH(c);
     NPB_CUDA(cudaStreamSynchronize(c->stream));
     c->have_flags = true;

@@ -117,14 +117,19 @@ struct npb_ctx {
     void *gls_ws = nullptr;
     size_t gls_ws_cap = 0;
     int *counters = nullptr;     // small device int array (work counters, flags)
+    int *h_small = nullptr, *d_small = nullptr;   // 64 ints of mapped page-locked memory: counts a kernel hands to the host
+                                                  // without a D2H copy (small copies queue behind bulk downloads on the copy engine)
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;  // npb_timer_start / stop
     void *stage[2] = {nullptr, nullptr};         // page-locked staging buffers for pageable host memory
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    cudaStream_t up_stream = nullptr, down_stream = nullptr;   // stream.cu: upload / download legs of the pipeline
+    std::vector<cudaEvent_t> pipe_ev;
 };
 
 // ---- helpers implemented in capi.cu ----
 int npb_alloc(npb_ctx *c, void **p, size_t bytes, bool owned_by_mesh = true);
 int npb_ensure(void **p, size_t *cap, size_t bytes);
+bool npb_is_pinned(const void *p);
 int npb_h2d(npb_ctx *c, void *dst_dev, const void *src_host, size_t bytes);
 int npb_d2h(npb_ctx *c, void *dst_host, const void *src_dev, size_t bytes);
 struct NpbTimer {
@@ -153,6 +158,7 @@ int npb_k2_idw_ls_tiles(npb_ctx *c, int method, i64 lo, i64 hi, int *used);
 int npb_ensure_out(npb_ctx *c, size_t n);
 int npb_k2_gls(npb_ctx *c, i64 lo, i64 hi);
 int npb_k3_fill(npb_ctx *c, i64 lo, i64 hi);
+int npb_read_int(npb_ctx *c, const int *d_src, int *h_out);   // device int -> host through the mapped block + stream sync
 int npb_minmax_i32(npb_ctx *c, const int32_t *in, i64 n, int32_t *h_min, int32_t *h_max);
 int npb_k4_gather_counts(npb_ctx *c);
 int npb_k4_gather_blocks(npb_ctx *c);

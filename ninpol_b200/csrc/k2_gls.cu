@@ -1124,8 +1124,7 @@ int npb_k2_gls(npb_ctx *c, i64 lo, i64 hi)
         NPB_TRY(npb_select_class(c, cls, lo, hi, MF_NCLASS - 1, list, &n_dense_direct));
         NPB_TRY(npb_gls_dense(c, a, list, n_dense_direct));
         int h_over = 0;
-        NPB_CUDA(cudaMemcpyAsync(&h_over, n_overflow, sizeof(int), cudaMemcpyDeviceToHost, s));
-        NPB_CUDA(cudaStreamSynchronize(s));
+        NPB_TRY(npb_read_int(c, n_overflow, &h_over));
         NPB_TRY(npb_gls_dense(c, a, overflow, h_over));
         tk.stop();
         c->timings["gls_dense_nodes"] = (float)(n_dense_direct + h_over);

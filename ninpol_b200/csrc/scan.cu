@@ -73,14 +73,14 @@ int npb_select_class(npb_ctx *c, const uint8_t *cls, i64 lo, i64 hi, int which, 
     if (hi <= lo) return NPB_OK;
     thrust::counting_iterator<int> it((int)lo);
     ClassIs pred{cls, which};
-    int *d_num = c->counters + 17;
+    int *d_num = c->d_small + 1;   // mapped host memory: the count needs no D2H copy
     size_t need = 0;
     NPB_CUDA(cub::DeviceSelect::If(nullptr, need, it, out, d_num, (int)(hi - lo), pred, c->stream));
     NPB_TRY(npb_ensure(&c->scratch, &c->scratch_cap, need));
     NPB_CUDA(cub::DeviceSelect::If(c->scratch, need, it, out, d_num, (int)(hi - lo), pred, c->stream));
     c->launches += 2;
-    NPB_CUDA(cudaMemcpyAsync(host_count, d_num, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     NPB_CUDA(cudaStreamSynchronize(c->stream));
+    *host_count = c->h_small[1];
     return NPB_OK;
 }
 

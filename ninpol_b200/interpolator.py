@@ -73,7 +73,7 @@ class _Method:
 
 class Interpolator:
     def __init__(self, name="interpolator", logging=False, build_edges=False, device=None, comm=None,
-                 pinned_outputs=False, pin_inputs=False, gather="all"):
+                 pinned_outputs=False, pin_inputs=False, gather="all", stream_chunks=0):
         # pinned_outputs=True: the CSR / neumann arrays returned by interpolate() live in page-locked
         # buffers that are REUSED by the next interpolate() call (faster device->host copies)
         self.pinned_outputs = pinned_outputs
@@ -116,6 +116,10 @@ class Interpolator:
         if gather not in ("all", "root"):
             raise ValueError("gather must be 'all' or 'root'")
         self.gather = gather
+        # stream_chunks=K > 0 (single GPU, needs pinned_outputs and pin_inputs): interpolate() runs as a
+        # pipeline over K node chunks - uploads of the GLS cell fields and downloads of the CSR blocks
+        # overlap the kernels (npb_interpolate_streamed); results are bit-identical to the plain path
+        self.stream_chunks = int(stream_chunks)
         if self.comm.world > 1:
             self._ctx.comm_init(self.comm.unique_id, self.comm.rank, self.comm.world)
             self._ctx.set_gather(gather)
@@ -357,7 +361,7 @@ class Interpolator:
             raise ValueError("target_points subsets are not supported: the reference builds an inconsistent "
                              "(n_target, n_elems) matrix for them and fails in scipy; pass all nodes or nothing")
 
-    def _stage_inputs(self, method, variable, variable_to_index, cells_data, points_data):
+    def _stage_inputs(self, method, variable, variable_to_index, cells_data, points_data, defer_fields=False):
         """Uploads what the plug-in of `method` reads for `variable` (idw.pyx:27-28, ls.pyx:28-29,
         gls.pyx:47-59).  Missing names raise KeyError like the reference's dict lookups."""
         g = self.grid
@@ -371,8 +375,12 @@ class Interpolator:
         else:
             flag_index = variable_to_index["points"]["neumann_flag_" + variable]
         if self._staged == key:
-            return
-        flags = np.asarray(points_data[flag_index])[:g.n_points].astype(DTYPE_I)
+            return None
+        flags = np.asarray(points_data[flag_index])[:g.n_points]
+        if flags.dtype == DTYPE_F and flags.flags.c_contiguous:
+            flags = self._maybe_pin("neumann_flag", flags)     # truncated like .astype(int) on the device
+        else:
+            flags = flags.astype(DTYPE_I)
         self._ctx.set_point_flags(flags)
         self._flags_host = flags
         self._staged = key
@@ -381,7 +389,11 @@ class Interpolator:
         if method == "gls":
             perm = np.ascontiguousarray(np.asarray(cells_data[permeability_index])[:g.n_elems * 9], dtype=DTYPE_F)
             dm = np.ascontiguousarray(np.asarray(cells_data[diff_mag_index])[:g.n_elems], dtype=DTYPE_F)
-            perm, dm = self._maybe_pin("permeability", perm), self._maybe_pin("diff_mag", dm)
+            perm, dm = self._maybe_pin("permeability", perm, defer_fields), self._maybe_pin("diff_mag", dm, defer_fields)
+            if defer_fields and "permeability" in self._registered and "diff_mag" in self._registered:
+                # the streamed pipeline uploads them slice by slice, overlapped with the kernels
+                self.last_timings["h2d_input_bytes"] = h2d + perm.nbytes + dm.nbytes
+                return perm, dm
             if self.comm.world > 1:
                 # a rank's nodes read the cell fields of the elements in their own esup rows only
                 first, last = self._ctx.partition_elem_range()
@@ -394,9 +406,10 @@ class Interpolator:
                 self._ctx.set_cell_field("diff_mag", dm)
                 h2d += perm.nbytes + dm.nbytes
         self.last_timings["h2d_input_bytes"] = h2d
+        return None
 
-    def _maybe_pin(self, name, arr):
-        if not self.pin_inputs or arr.nbytes < (8 << 20):
+    def _maybe_pin(self, name, arr, force=False):
+        if not self.pin_inputs or (arr.nbytes < (8 << 20) and not force) or arr.nbytes == 0:
             return arr
         reg = self._registered.get(name)
         if reg is None or reg.array is None or reg.array.ctypes.data != arr.ctypes.data or reg.array.nbytes != arr.nbytes:
@@ -429,7 +442,7 @@ class Interpolator:
             return
         g = self.grid
         E = np.diff(np.asarray(g.esup_ptr))
-        processed = ~((np.asarray(g.boundary_points) != 0) & (self._flags_host == 0))
+        processed = ~((np.asarray(g.boundary_points) != 0) & (self._flags_host.astype(DTYPE_I) == 0))
         bounds = _dist.partition_nodes(_dist.node_cost(method, E, processed), self.comm.world)
         self._ctx.set_partition(bounds)
         self._partition_key = key
@@ -443,6 +456,18 @@ class Interpolator:
             buf = _capi.pinned_empty(n + n // 16 + 16, dtype)
             self._pinned[name] = buf
         return buf[:n]
+
+    def _run_streamed(self, method, fields):
+        g = self.grid
+        n_points, cap = g.n_points, max(1, self._ctx.scalar("len_esup"))
+        indptr = self._out("indptr", n_points + 1, np.int32)
+        indices = self._out("indices", cap, np.int32)
+        data = self._out("data", cap, np.float64)
+        neumann = self._out("neumann", n_points, np.float64)
+        perm, dm = fields if fields is not None else (None, None)
+        nnz = self._ctx.interpolate_streamed(method, self.stream_chunks, perm, dm, indptr, indices, data, neumann)
+        self.last_timings.update({"streamed_ms": self._ctx.timing_or("streamed"), "nnz": nnz})
+        return indptr, indices[:nnz], data[:nnz], neumann
 
     def _run(self, method):
         g = self.grid
@@ -472,8 +497,13 @@ class Interpolator:
             raise ValueError(f"Variable '{variable}' has more than one dimension. Vector data not supported yet.")
         self._check_targets(target_points)
         self.logger.log(f"Interpolating variable '{variable}' using method '{method}'")
-        self._stage_inputs(method, variable, self.variable_to_index, self._rows["cells"], self._rows["points"])
-        indptr, indices, data, neumann = self._run(method)
+        streamed = self.stream_chunks > 0 and self.comm.world == 1 and self.pinned_outputs and self.pin_inputs
+        fields = self._stage_inputs(method, variable, self.variable_to_index, self._rows["cells"], self._rows["points"],
+                                    defer_fields=streamed)
+        if streamed:
+            indptr, indices, data, neumann = self._run_streamed(method, fields)
+        else:
+            indptr, indices, data, neumann = self._run(method)
         g = self.grid
         # the device emitted canonical CSR (sorted, zero-free, int32 index arrays): no conversion, no copy
         W = sp.csr_matrix((data, indices, indptr), shape=(g.n_points, g.n_elems), copy=False)
