@@ -223,6 +223,19 @@ __device__ __forceinline__ void mf_store_cb(const double *src, int sld, int rows
 // Householder scalars of one column: alpha = -sign(x0) |x|, beta = 2 / |v|^2 with v = x - alpha e1, and
 // rinv = 1 / alpha (kept on the diagonal of R for the back substitution).  sqrt and 1/alpha come from one
 // rsqrt plus a Newton step instead of the IEEE sqrt and divide sequences.
+// MUFU seeds (upper-word approximations, ~20 bits) for 1/sqrt(x) and 1/x; refined below with Newton steps.
+__device__ __forceinline__ double rsqrt_seed(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+__device__ __forceinline__ double rcp_seed(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
 __device__ __forceinline__ void hh_scalars(double sigma, double x0, double &alpha, double &beta, double &rinv)
 {
     if (sigma == 0.0) {   // zero column: identity reflector, zero pivot (NaN takes the normal path and propagates)
@@ -231,13 +244,23 @@ __device__ __forceinline__ void hh_scalars(double sigma, double x0, double &alph
         rinv = 0.0;
         return;
     }
-    double rs = rsqrt(sigma);
-    double sq = sigma * rs;
-    sq = fma(fma(-sq, sq, sigma), 0.5 * rs, sq);   // sq -> sqrt(sigma) to the last bit or so
-    rs = fma(fma(-sq, rs, 1.0), rs, rs);           // rs -> 1 / sq
+    // sqrt(sigma), 1/sqrt(sigma) and 1/(sigma + |x0| sqrt(sigma)) from two hardware seeds and Newton steps:
+    // a third of the instructions of the IEEE rsqrt / reciprocal sequences, accurate to an ulp or two
+    const double h = 0.5 * sigma;
+    double y = rsqrt_seed(sigma);
+    y = y * fma(-h * y, y, 1.5);
+    y = y * fma(-h * y, y, 1.5);
+    double sq = sigma * y;
+    sq = fma(fma(-sq, sq, sigma), 0.5 * y, sq);   // sq -> sqrt(sigma)
+    const double rs = fma(fma(-sq, y, 1.0), y, y); // rs -> 1 / sq
     alpha = (x0 >= 0.0) ? -sq : sq;
     rinv = (x0 >= 0.0) ? -rs : rs;
-    beta = __drcp_rn(sigma - x0 * alpha);
+    const double den = fma(fabs(x0), sq, sigma);   // sigma - x0 * alpha
+    double r = rcp_seed(den);
+    r = r * fma(-den, r, 2.0);
+    r = r * fma(-den, r, 2.0);
+    r = fma(fma(-den, r, 1.0), r, r);
+    beta = r;
 }
 
 // returns 0 on success, 1 when the star does not fit this class (caller reroutes it to the dense kernel)
