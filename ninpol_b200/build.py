@@ -18,6 +18,7 @@ LIB = os.path.join(HERE, "libninpol_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-ccbin", "/usr/bin/g++"]
+EXTRA = os.environ.get("NPB_NVCC_EXTRA", "").split()   # experiments: e.g. -DLS_ECAP=1280 (use with --force)
 UNITS = {
     "capi.cu": [],
     "scan.cu": [],
@@ -52,7 +53,7 @@ def build(force=False, verbose=False):
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            jobs.append([NVCC] + ARCH + COMMON + extra + ["-c", s, "-o", o])
+            jobs.append([NVCC] + ARCH + COMMON + extra + EXTRA + ["-c", s, "-o", o])
 
     def run(cmd):
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

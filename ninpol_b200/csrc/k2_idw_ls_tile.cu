@@ -21,8 +21,21 @@
 
 #define TILE_NB 64
 #define TILE_T 256
+#ifndef IDW_ECAP
 #define IDW_ECAP 1536
+#endif
+#ifndef LS_ECAP
 #define LS_ECAP 1408
+#endif
+#ifndef LS_MINB
+#define LS_MINB 4   // 4 blocks of 46.8 KB fit an SM; 64 registers, no spills (5 would need <= 51)
+#endif
+#ifndef LS_ECAP_WIDE
+#define LS_ECAP_WIDE 1024
+#endif
+#ifndef LS_NB_WIDE
+#define LS_NB_WIDE 128
+#endif
 #define IDW_EPS ((double)1.0000000036274937e-15f) /* float32(1e-15), idw.pyx:53 */
 
 // rowcnt[p] = entries node p will emit if no weight is an exact zero; neumann[p] = 0
@@ -58,14 +71,15 @@ struct TileArgs {
     int direct;          // 1: write the CSR at indptr[] positions and count exact zeros; 0: two-pass mode
 };
 
+template <int NBCAP>
 __global__ void __launch_bounds__(TILE_T, 7) k_idw_tile(TileArgs a)
 {
-    __shared__ double s_r[IDW_ECAP + TILE_NB];
+    __shared__ double s_r[IDW_ECAP + NBCAP];
     __shared__ int s_e[IDW_ECAP];
     __shared__ unsigned char s_rid[IDW_ECAP];
-    __shared__ double s_x[TILE_NB * 3], s_tot[TILE_NB];
-    __shared__ int s_ptr[TILE_NB + 1], s_out[TILE_NB], s_fz[TILE_NB], s_cnt[TILE_NB];
-    __shared__ unsigned char s_proc[TILE_NB];
+    __shared__ double s_x[NBCAP * 3], s_tot[NBCAP];
+    __shared__ int s_ptr[NBCAP + 1], s_out[NBCAP], s_fz[NBCAP], s_cnt[NBCAP];
+    __shared__ unsigned char s_proc[NBCAP];
     const int tid = threadIdx.x;
     const i64 ntiles = (a.p_hi - a.p_lo + a.nb - 1) / a.nb;
     for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -160,14 +174,18 @@ __global__ void __launch_bounds__(TILE_T, 7) k_idw_tile(TileArgs a)
 #define S2(a, b) __dsub_rn(a, b)
 #define A2(a, b) __dadd_rn(a, b)
 
-__global__ void __launch_bounds__(TILE_T, 5) k_ls_tile(TileArgs a)
+// NBCAP = node capacity of a tile: 64 for stars of >= 22 elements (tets); 128 (with 1024 entries) for small
+// stars such as the 8 hexes around a node, where 64 nodes would use a third of the entry capacity and leave
+// 3/4 of the threads idle in phase B (hex 200^3: 1.53 -> 1.08 ms)
+template <int ECAP, int NBCAP>
+__global__ void __launch_bounds__(TILE_T, LS_MINB) k_ls_tile(TileArgs a)
 {
-    __shared__ double s_vx[LS_ECAP + TILE_NB], s_vy[LS_ECAP + TILE_NB], s_vz[LS_ECAP + TILE_NB];
-    __shared__ int s_e[LS_ECAP];
-    __shared__ unsigned char s_rid[LS_ECAP];
-    __shared__ double s_x[TILE_NB * 3], s_lam[TILE_NB * 4];
-    __shared__ int s_ptr[TILE_NB + 1], s_out[TILE_NB], s_cnt[TILE_NB];
-    __shared__ unsigned char s_proc[TILE_NB], s_mode[TILE_NB];
+    __shared__ double s_vx[ECAP + NBCAP], s_vy[ECAP + NBCAP], s_vz[ECAP + NBCAP];
+    __shared__ int s_e[ECAP];
+    __shared__ unsigned char s_rid[ECAP];
+    __shared__ double s_x[NBCAP * 3], s_lam[NBCAP * 4];
+    __shared__ int s_ptr[NBCAP + 1], s_out[NBCAP], s_cnt[NBCAP];
+    __shared__ unsigned char s_proc[NBCAP], s_mode[NBCAP];
     const int tid = threadIdx.x;
     const i64 ntiles = (a.p_hi - a.p_lo + a.nb - 1) / a.nb;
     for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -274,13 +292,23 @@ __global__ void __launch_bounds__(TILE_T, 5) k_ls_tile(TileArgs a)
     }
 }
 
+// nodes per tile; > TILE_NB selects the small-star LS variant (128 nodes x 1024 entries)
 static int tile_nb(npb_ctx *c, int method)
 {
-    const int ecap = method == NPB_METHOD_IDW ? IDW_ECAP : LS_ECAP;
     if (c->mx_epp <= 0) return 0;
     const char *force = getenv("NPB_FORCE_SIMPLE_IDW_LS");   // tests: exercise the thread-per-node kernels
     if (force && force[0] == '1') return 0;
-    int nb = ecap / c->mx_epp;
+    const char *nowide = getenv("NPB_TILE_NO_WIDE");          // A/B timing: 64-node tiles only
+    const bool wide_ok = !(nowide && nowide[0] == '1');
+    if (method == NPB_METHOD_IDW) {   // measured: 192-node IDW tiles are 25 % slower than 64-node ones on hex meshes
+        int nb = IDW_ECAP / c->mx_epp;
+        return nb > TILE_NB ? TILE_NB : nb;
+    }
+    int nb = LS_ECAP / c->mx_epp;
+    if (nb > TILE_NB && wide_ok) {
+        int nw = LS_ECAP_WIDE / c->mx_epp;
+        return nw > LS_NB_WIDE ? LS_NB_WIDE : nw;
+    }
     return nb > TILE_NB ? TILE_NB : nb;
 }
 
@@ -298,10 +326,14 @@ static int tile_launch(npb_ctx *c, const TileArgs &a, int method)
     int grid = (int)(ntiles < (i64)c->sm_count * 8 ? ntiles : (i64)c->sm_count * 8);
     if (grid < 1) return NPB_OK;
     NpbTimer tm(c, "k2_main");
-    if (method == NPB_METHOD_IDW)
-        k_idw_tile<<<grid, TILE_T, 0, c->stream>>>(a);
-    else
-        k_ls_tile<<<grid, TILE_T, 0, c->stream>>>(a);
+    if (method == NPB_METHOD_IDW) {
+        k_idw_tile<TILE_NB><<<grid, TILE_T, 0, c->stream>>>(a);
+    } else {
+        if (a.nb > TILE_NB)
+            k_ls_tile<LS_ECAP_WIDE, LS_NB_WIDE><<<grid, TILE_T, 0, c->stream>>>(a);
+        else
+            k_ls_tile<LS_ECAP, TILE_NB><<<grid, TILE_T, 0, c->stream>>>(a);
+    }
     NPB_LAUNCH(c);
     NPB_CUDA(cudaGetLastError());
     tm.stop();
