@@ -296,7 +296,7 @@ def timed_e2e_steps(I, plumb, method, steps, warmup):
     # bytes actually copied per step, summed over the ranks (a GLS rank uploads the slice of the cell
     # fields its nodes read; with gather="root" only rank 0 downloads the whole CSR)
     h2d = plumb.sum(I.last_timings["h2d_input_bytes"])
-    d2h = plumb.sum(W.indptr.nbytes + W.indices.nbytes + W.data.nbytes + nv.nbytes)
+    d2h = plumb.sum(I.last_timings["d2h_bytes"])
     return plumb.max(dt) / steps, int(h2d), int(d2h)
 
 
@@ -314,7 +314,7 @@ def run_ours(args, rank, world):
     if rank == 0:
         log(f"mesh {desc}: generated in {time.time() - t0:.1f}s")
     t0 = time.time()
-    I = ninpol_b200.Interpolator(comm=comm, pinned_outputs=True, pin_inputs=True, gather="root",
+    I = ninpol_b200.Interpolator(comm=comm, pinned_outputs=True, pin_inputs=True, gather=args.gather,
                                  stream_chunks=args.stream_chunks if world == 1 else 0)
     I.load_mesh(mesh_obj=mesh)
     t_load = time.time() - t0
@@ -326,8 +326,16 @@ def run_ours(args, rank, world):
         log(f"load_mesh {t_load:.2f}s wall; device K1 {k1['k1']:.1f} ms (esup {k1['k1_esup']:.1f}, esuel {k1['k1_esuel']:.1f}, "
             f"faces {k1['k1_faces']:.1f}, fsup {k1['k1_fsup']:.1f}, geom {k1['k1_geom']:.1f}); H2D {k1['h2d_mesh']:.1f} ms")
     method = args.method
-    W0, _ = I.interpolate(VARIABLE, method)      # stages the inputs, sets the partition
-    nnz = int(np.asarray(g.esup_ptr)[-1]) if world > 1 and rank != 0 else W0.nnz   # only rank 0 prints it
+    try:
+        W0, _ = I.interpolate(VARIABLE, method)      # stages the inputs, sets the partition
+    except Exception as e:                          # /dev/shm too small on this box (every rank sees the same)
+        if world > 1 and args.gather == "host" and "gather='host'" in str(e):
+            args.gather = "root"
+            I.set_gather("root")
+            W0, _ = I.interpolate(VARIABLE, method)
+        else:
+            raise
+    nnz = W0.nnz   # only rank 0 prints it (gather="root": the other ranks hold their own block)
     del W0
     sampler = ClockSampler(ctx.device) if rank == 0 else None
     ms_step, k2_ms, main_ms, launches, clocks = timed_device_steps(I, plumb, method, args.steps, max(args.warmup, 3), sampler)
@@ -348,14 +356,15 @@ def run_ours(args, rank, world):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc, "method": method, "n_nodes": n_points, "n_cells": n_elems, "nnz": nnz,
-                   "processed_nodes": n_proc, "partition": f"nodes split into {world} contiguous cost-balanced ranges; mesh replicated; row blocks gathered to rank 0",
+                   "processed_nodes": n_proc, "partition": f"nodes split into {world} contiguous cost-balanced ranges; mesh replicated; e2e gather='{args.gather}'",
                    "cache": "inputs larger than L2 (working set >> 126 MB); no flush needed" if n_elems > 2_000_000 else
                             "small workload: L2-resident between iterations"},
         "e2e": {"value": n_points / e2e_s, "unit": "nodes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_s * 1e3, "api": f"Interpolator(pinned_outputs=True, pin_inputs=True, gather='root', stream_chunks={args.stream_chunks if world == 1 else 0}).interpolate(variable, method) after "
+                "ms_per_step": e2e_s * 1e3, "api": f"Interpolator(pinned_outputs=True, pin_inputs=True, gather='{args.gather}', stream_chunks={args.stream_chunks if world == 1 else 0}).interpolate(variable, method) after "
                 "invalidate_inputs(): H2D of flags (+ the slice of permeability / diff_mag this rank's nodes read) from page-locked "
-                "host arrays + K2 + K3 (+ K4: row blocks to rank 0 over NCCL) + D2H of the CSR (rank 0: all of it; other ranks: "
-                "their own rows) into page-locked numpy buffers, scipy.csr_matrix wrap; byte counts are sums over ranks; stream_chunks > 0 (1 GPU): the three legs run as a pipeline over node chunks"},
+                "host arrays + K2 + K3 + (N > 1) K4: row counts all-gathered over NCCL, then gather='host': every rank copies its CSR rows "
+                "into one page-locked host mapping shared by the ranks (/dev/shm), NCCL barrier; gather='root': row blocks to rank 0 over "
+                "NCCL, rank 0 downloads the CSR; scipy.csr_matrix wrap; byte counts are sums over ranks; stream_chunks > 0 (1 GPU): the three legs run as a pipeline over node chunks"},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_gls_mf (largest size class)" if method == "gls" else f"k_{method}",
@@ -426,6 +435,8 @@ def main():
     ap.add_argument("--n", type=int, default=0, help="override the lattice size of the workload (debug)")
     ap.add_argument("--ref-n", type=int, default=0, help="lattice size of the CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--gather", default="host", choices=["host", "root", "all"],
+                    help="N > 1: where the row blocks meet (host: shared host mapping; root: rank 0's GPU; all: every GPU)")
     ap.add_argument("--stream-chunks", type=int, default=8,
                     help="e2e at 1 GPU: node chunks of the upload / compute / download pipeline (0 = plain count + fetch)")
     args = ap.parse_args()

@@ -63,7 +63,16 @@ int npb_set_partition(npb_ctx *ctx, const int64_t *bounds, int n_bounds);
  * npb_interpolate_fetch then return their own row block (rows of other ranks empty, shape unchanged). */
 #define NPB_GATHER_ALL 0
 #define NPB_GATHER_ROOT 1
+/* NPB_GATHER_HOST: no device-side gather of the blocks at all - npb_interpolate_count reports the global nnz
+ * on every rank and npb_interpolate_fetch copies THIS RANK'S rows to their global positions in the arrays it
+ * is given (indptr[lo..hi), indices / data [indptr[lo], indptr[hi]), neumann[lo..hi); the last rank also
+ * writes indptr[n_points]).  When all ranks pass views of one shared host mapping, the full CSR assembles
+ * in host memory through eight PCIe links in parallel; npb_comm_barrier separates the steps. */
+#define NPB_GATHER_HOST 2
 int npb_set_gather(npb_ctx *ctx, int mode);
+/* All ranks of the communicator have reached this call and their streams are idle (a grouped 1-int
+ * ncclBroadcast from every rank).  No-op when world == 1. */
+int npb_comm_barrier(npb_ctx *ctx);
 /* Closed range [first, last] of the element ids that occur in the node->element rows of this rank's node
  * range (after npb_set_partition): the only elements whose cell fields the rank's nodes read, so a rank
  * needs to upload just that slice (npb_set_cell_field_range).  first > last for an empty node range. */

@@ -25,6 +25,7 @@ _SIGNATURES = {
     "npb_comm_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
     "npb_set_partition": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "npb_set_gather": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "npb_comm_barrier": (ctypes.c_int, [ctypes.c_void_p]),
     "npb_partition_elem_range": (ctypes.c_int, [ctypes.c_void_p, _c_i64p, _c_i64p]),
     "npb_set_cell_field_range": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64]),
     "npb_load_mesh": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64] + [ctypes.c_void_p] * 9 + [ctypes.c_int]),
@@ -129,7 +130,10 @@ class Context:
 
     def set_gather(self, mode):
         """'all': every rank receives the full CSR; 'root': rank 0 only, the others keep their row block."""
-        check(self.lib.npb_set_gather(self.handle, {"all": 0, "root": 1}[mode]))
+        check(self.lib.npb_set_gather(self.handle, {"all": 0, "root": 1, "host": 2}[mode]))
+
+    def comm_barrier(self):
+        check(self.lib.npb_comm_barrier(self.handle))
 
     def partition_elem_range(self):
         """Closed range of the element ids this rank's nodes touch (first > last when it owns no node)."""

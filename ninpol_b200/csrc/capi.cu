@@ -314,8 +314,8 @@ extern "C" int npb_set_partition(npb_ctx *c, const int64_t *bounds, int n_bounds
 
 extern "C" int npb_set_gather(npb_ctx *c, int mode)
 {
-    if (!c || (mode != NPB_GATHER_ALL && mode != NPB_GATHER_ROOT)) {
-        npb_set_error("npb_set_gather: mode must be NPB_GATHER_ALL or NPB_GATHER_ROOT");
+    if (!c || (mode != NPB_GATHER_ALL && mode != NPB_GATHER_ROOT && mode != NPB_GATHER_HOST)) {
+        npb_set_error("npb_set_gather: mode must be NPB_GATHER_ALL, NPB_GATHER_ROOT or NPB_GATHER_HOST");
         return NPB_ERR_ARG;
     }
     c->gather_mode = mode;
@@ -735,10 +735,27 @@ extern "C" int npb_interpolate_fetch(npb_ctx *c, int32_t *indptr, int32_t *indic
         tm.stop();
         c->filled = true;
     }
-    if (c->world > 1) {
+    const bool host_gather = c->world > 1 && c->gather_mode == NPB_GATHER_HOST;
+    if (c->world > 1 && !host_gather) {
         NpbTimer tm(c, "k4_gather");
         NPB_TRY(npb_k4_gather_blocks(c));
         tm.stop();
+    }
+    if (host_gather) {
+        // this rank's rows to their global positions of the (shared) host arrays
+        NpbTimer tm(c, "d2h_csr");
+        int32_t o[2] = {0, 0};
+        NPB_TRY(npb_read_int(c, c->indptr + c->lo, &o[0]));
+        NPB_TRY(npb_read_int(c, c->indptr + c->hi, &o[1]));
+        const i64 rows = c->hi - c->lo, nk = (i64)o[1] - o[0];
+        const i64 extra = (c->rank == c->world - 1) ? 1 : 0;   // the closing indptr entry
+        if (indptr && rows + extra > 0) NPB_TRY(npb_d2h(c, indptr + c->lo, c->indptr + c->lo, sizeof(int32_t) * (size_t)(rows + extra)));
+        if (indices && nk > 0) NPB_TRY(npb_d2h(c, indices + o[0], c->indices + o[0], sizeof(int32_t) * (size_t)nk));
+        if (data && nk > 0) NPB_TRY(npb_d2h(c, data + o[0], c->data + o[0], sizeof(double) * (size_t)nk));
+        if (neumann && rows > 0) NPB_TRY(npb_d2h(c, neumann + c->lo, c->neumann + c->lo, sizeof(double) * (size_t)rows));
+        tm.stop();
+        NPB_CUDA(cudaStreamSynchronize(s));
+        return NPB_OK;
     }
     {
         NpbTimer tm(c, "d2h_csr");

@@ -114,6 +114,25 @@ int npb_comm_destroy(npb_ctx *c)
     return NPB_OK;
 }
 
+extern "C" int npb_comm_barrier(npb_ctx *c)
+{
+    if (!c) return NPB_ERR_ARG;
+    if (c->world == 1) return NPB_OK;
+    NPB_CUDA(cudaSetDevice(c->device));
+    NcclApi *api = c->nccl;
+    ncclComm_t comm = (ncclComm_t)c->comm;
+    int *buf = c->counters + 48;   // 16 ints: one per rank (world <= 16 on one box)
+    if (c->world > 16) {
+        npb_set_error("npb_comm_barrier: world > 16 not supported");
+        return NPB_ERR_ARG;
+    }
+    NPB_NCCL(api->GroupStart());
+    for (int r = 0; r < c->world; r++) NPB_NCCL(api->Broadcast(buf + r, buf + r, 1, ncclInt32, r, comm, c->stream));
+    NPB_NCCL(api->GroupEnd());
+    NPB_CUDA(cudaStreamSynchronize(c->stream));
+    return NPB_OK;
+}
+
 // all-gather of rowcnt[lo_r:hi_r] and neumann[lo_r:hi_r] from their owners
 int npb_k4_gather_counts(npb_ctx *c)
 {

@@ -5,6 +5,8 @@ the host logic that is independent of CUDA and therefore testable on CPU: readin
 environment, shipping the 128-byte NCCL unique id from rank 0 to the other ranks over a plain TCP
 socket, and cutting the node range into contiguous per-rank blocks balanced on a cost prefix sum.
 """
+import hashlib
+import mmap
 import os
 import socket
 import struct
@@ -125,3 +127,78 @@ def assemble_row_blocks(blocks, n_points):
         indices[s:e] = b["indices"]
         data[s:e] = b["data"]
     return indptr.astype(np.int32), indices, data, neumann
+
+
+class _ExactView:
+    """Array-interface owner of exactly n items inside a mapping.  scipy copies an index / data array that is
+    a view of a base more than twice its size (`_prune_array`); a view that owns its exact extent is kept."""
+
+    def __init__(self, address, n, dtype, keepalive):
+        self.size = int(n)
+        self._keepalive = keepalive
+        self.__array_interface__ = {"shape": (int(n),), "typestr": np.dtype(dtype).str, "data": (int(address), False),
+                                    "version": 3}
+
+
+class SharedOutputs:
+    """One host mapping shared by the ranks of a box, holding the CSR arrays of gather="host":
+    indptr [n_points+1] int32 | neumann [n_points] f64 | indices [cap] int32 | data [cap] f64 (4 KiB aligned).
+
+    Rank 0 creates `/dev/shm/<name>` (create()), the others open it (attach()) once rank 0 is known to be
+    done - the caller separates the two with a barrier - and rank 0 unlinks the name after a second barrier,
+    so the segment disappears with the last process.  Every rank writes only its own rows."""
+
+    DIR = "/dev/shm"
+
+    def __init__(self, token, n_points, cap):
+        self.n_points, self.cap = int(n_points), max(1, int(cap))
+        al = lambda x: (x + 4095) & ~4095
+        self.off_indptr = 0
+        self.off_neumann = al(4 * (self.n_points + 1))
+        self.off_indices = self.off_neumann + al(8 * self.n_points)
+        self.off_data = self.off_indices + al(4 * self.cap)
+        self.nbytes = self.off_data + al(8 * self.cap)
+        self.path = os.path.join(self.DIR, "npb_" + hashlib.sha1(token).hexdigest()[:24])
+        self.mm = None
+
+    @classmethod
+    def fits(cls, nbytes):
+        try:
+            st = os.statvfs(cls.DIR)
+        except OSError:
+            return False
+        return st.f_bavail * st.f_frsize > nbytes + (64 << 20)
+
+    def _map(self, fd):
+        self.mm = mmap.mmap(fd, self.nbytes, mmap.MAP_SHARED, mmap.PROT_READ | mmap.PROT_WRITE)
+        os.close(fd)
+        self.buf = np.frombuffer(self.mm, dtype=np.uint8)
+        self.indptr = self.buf[self.off_indptr:self.off_indptr + 4 * (self.n_points + 1)].view(np.int32)
+        self.neumann = self.buf[self.off_neumann:self.off_neumann + 8 * self.n_points].view(np.float64)
+        self.indices = self.buf[self.off_indices:self.off_indices + 4 * self.cap].view(np.int32)
+        self.data = self.buf[self.off_data:self.off_data + 8 * self.cap].view(np.float64)
+
+    def exact(self, name, n):
+        """The first n items of indptr / indices / data / neumann as an array that is not a view of a larger one."""
+        full = getattr(self, name)
+        if n == full.size:
+            n = full.size
+        return np.asarray(_ExactView(full.ctypes.data, n, full.dtype, self.mm))
+
+    def create(self):
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        fd = os.open(self.path, os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+        os.ftruncate(fd, self.nbytes)
+        self._map(fd)
+
+    def attach(self):
+        self._map(os.open(self.path, os.O_RDWR))
+
+    def unlink(self):
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass

@@ -13,6 +13,7 @@ loops, same outputs) and hands plain arrays to libninpol_b200.so through ctypes;
 geometry, the per-node weights and the CSR emit all run on the GPU.  There is no CPU fallback.
 """
 import os
+import struct
 import pickle
 import tempfile
 import time
@@ -112,9 +113,12 @@ class Interpolator:
             device = self.comm.local_rank if self.comm.world > 1 else 0
         self._ctx = _capi.Context(device)      # raises when the library or the GPU is missing
         # gather="all": every rank returns the full CSR; gather="root": rank 0 does, the other ranks
-        # return the rows they own (other rows empty) and the blocks travel to rank 0 only
-        if gather not in ("all", "root"):
-            raise ValueError("gather must be 'all' or 'root'")
+        # return the rows they own (other rows empty) and the blocks travel to rank 0 only;
+        # gather="host": every rank copies its rows straight into one shared host mapping (/dev/shm), so the
+        # full CSR assembles through all PCIe links at once and every rank returns views of it - valid
+        # until any rank's next interpolate() / load_mesh()
+        if gather not in ("all", "root", "host"):
+            raise ValueError("gather must be 'all', 'root' or 'host'")
         self.gather = gather
         # stream_chunks=K > 0 (single GPU, needs pinned_outputs and pin_inputs): interpolate() runs as a
         # pipeline over K node chunks - uploads of the GLS cell fields and downloads of the CSR blocks
@@ -125,6 +129,7 @@ class Interpolator:
             self._ctx.set_gather(gather)
         self._staged = None
         self._partition_key = None
+        self._shared, self._shared_reg, self._mesh_serial = None, None, 0
         self.last_timings = {}
 
     def _dense_view(self, kind):
@@ -221,6 +226,8 @@ class Interpolator:
         self._registered = {}
         self._staged = None
         self._partition_key = None
+        self._shared, self._shared_reg = None, None      # gather="host": a new mapping per mesh
+        self._mesh_serial += 1
         self.logger.log(f"Mesh loaded successfully: {n_points} points and {n_elems} elements.")
         if not cached and filename != "":
             little_hash = hex(os.path.getsize(filename))
@@ -423,11 +430,35 @@ class Interpolator:
 
     def set_gather(self, gather):
         """Switch between gather="all" and gather="root" on a live communicator (see __init__)."""
-        if gather not in ("all", "root"):
-            raise ValueError("gather must be 'all' or 'root'")
+        if gather not in ("all", "root", "host"):
+            raise ValueError("gather must be 'all', 'root' or 'host'")
         self.gather = gather
         if self.comm.world > 1:
             self._ctx.set_gather(gather)
+
+    def _shared_outputs(self):
+        """The shared host mapping of gather="host" for the current mesh (created collectively on first use)."""
+        if self._shared is not None:
+            return self._shared
+        g = self.grid
+        token = bytes(self.comm.unique_id) + struct.pack("<q", self._mesh_serial)
+        so = _dist.SharedOutputs(token, g.n_points, self._ctx.scalar("len_esup"))
+        if not _dist.SharedOutputs.fits(so.nbytes):
+            raise _capi.NinpolB200Error(f"gather='host' needs {so.nbytes >> 20} MiB in {so.DIR}; use gather='root'")
+        if self.comm.rank == 0:
+            so.create()
+        self._ctx.comm_barrier()
+        if self.comm.rank != 0:
+            so.attach()
+        self._ctx.comm_barrier()
+        if self.comm.rank == 0:
+            so.unlink()                     # the mapping lives on; the name is gone
+        try:
+            self._shared_reg = _capi.HostRegistration(so.buf)   # page-lock this process's view: full-rate DMA
+        except _capi.NinpolB200Error:
+            self._shared_reg = None
+        self._shared = so
+        return so
 
     def invalidate_inputs(self):
         """Forget which per-variable inputs are resident on the device: the next interpolate() uploads
@@ -466,12 +497,26 @@ class Interpolator:
         neumann = self._out("neumann", n_points, np.float64)
         perm, dm = fields if fields is not None else (None, None)
         nnz = self._ctx.interpolate_streamed(method, self.stream_chunks, perm, dm, indptr, indices, data, neumann)
-        self.last_timings.update({"streamed_ms": self._ctx.timing_or("streamed"), "nnz": nnz})
+        self.last_timings.update({"streamed_ms": self._ctx.timing_or("streamed"), "nnz": nnz,
+                                  "d2h_bytes": indptr.nbytes + neumann.nbytes + 12 * nnz})
         return indptr, indices[:nnz], data[:nnz], neumann
 
     def _run(self, method):
         g = self.grid
         self._set_partition(method)
+        if self.comm.world > 1 and self.gather == "host":
+            so = self._shared_outputs()
+            self._ctx.comm_barrier()        # every rank is done with the arrays of the previous call
+            nnz = self._ctx.interpolate_count(method)
+            self._ctx.interpolate_fetch(so.indptr, so.indices, so.data, so.neumann)
+            self._ctx.comm_barrier()        # every block has landed
+            t = self._ctx.timing_or
+            self.last_timings.update({"k2_ms": t("k2"), "k3_count_ms": t("k3_count"), "k3_fill_ms": t("k3_fill"),
+                                      "k4_gather_ms": 0.0, "d2h_csr_ms": t("d2h_csr"), "nnz": nnz})
+            lo, hi = int(self.partition_bounds[self.comm.rank]), int(self.partition_bounds[self.comm.rank + 1])
+            self.last_timings["d2h_bytes"] = 12 * int(so.indptr[hi] - so.indptr[lo]) + 12 * (hi - lo)   # this rank's rows
+            return (so.exact("indptr", g.n_points + 1), so.exact("indices", nnz), so.exact("data", nnz),
+                    so.exact("neumann", g.n_points))
         nnz = self._ctx.interpolate_count(method)
         n_points = g.n_points
         indptr = self._out("indptr", n_points + 1, np.int32)
@@ -482,7 +527,8 @@ class Interpolator:
         t = self._ctx.timing_or
         self.last_timings.update({"k2_ms": t("k2"), "k3_count_ms": t("k3_count"), "k3_fill_ms": t("k3_fill"),
                                   "k4_gather_ms": t("k4_gather") if self.comm.world > 1 else 0.0,
-                                  "d2h_csr_ms": t("d2h_csr"), "nnz": nnz})
+                                  "d2h_csr_ms": t("d2h_csr"), "nnz": nnz,
+                                  "d2h_bytes": indptr.nbytes + indices.nbytes + data.nbytes + neumann.nbytes})
         return indptr, indices, data, neumann
 
     def interpolate(self, variable, method, target_points=np.array([], dtype=DTYPE_I)):

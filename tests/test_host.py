@@ -200,3 +200,33 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["value"] > 0 and d["e2e"]["value"] == d["value"]
+
+
+def test_shared_outputs_mapping_is_shared_and_disappears(tmp_path, monkeypatch):
+    """gather="host" plumbing: two mappings of one segment see each other's writes; after unlink the name
+    is gone but the mappings live on; the four arrays do not overlap."""
+    monkeypatch.setattr(dist.SharedOutputs, "DIR", str(tmp_path))
+    a = dist.SharedOutputs(b"token-1", n_points=1000, cap=5000)
+    b = dist.SharedOutputs(b"token-1", n_points=1000, cap=5000)
+    assert a.path == b.path and dist.SharedOutputs(b"token-2", 1000, 5000).path != a.path
+    assert dist.SharedOutputs.fits(a.nbytes)
+    a.create()
+    b.attach()
+    a.unlink()
+    assert not os.path.exists(a.path)
+    assert a.indptr.shape == (1001,) and a.indices.shape == (5000,) and a.data.shape == (5000,) and a.neumann.shape == (1000,)
+    a.indptr[:] = np.arange(1001)
+    a.indices[:] = 7
+    b.data[:] = 0.5
+    b.neumann[:] = -1.0
+    assert np.array_equal(b.indptr, np.arange(1001)) and np.all(b.indices == 7)
+    assert np.all(a.data == 0.5) and np.all(a.neumann == -1.0)
+    import scipy.sparse as sp
+    a.indptr[:] = 0
+    a.indptr[1:] = 3                      # one row of three entries
+    a.indices[:3] = [0, 1, 2]
+    W = sp.csr_matrix((a.exact("data", 3), a.exact("indices", 3), a.exact("indptr", 1001)), shape=(1000, 10), copy=False)
+    b.data[0] = 42.0                      # written through the other mapping: visible if scipy kept the view
+    assert W.data[0] == 42.0 and W.data.shape == (3,)
+    offs = [a.off_indptr, a.off_neumann, a.off_indices, a.off_data, a.nbytes]
+    assert offs == sorted(offs) and all(o % 4096 == 0 for o in offs)

@@ -4,7 +4,8 @@ Every rank holds the whole mesh and computes the CSR rows of its node range (GLS
 slice of the cell fields their nodes read).  gather="all": the row blocks are all-gathered over NCCL and
 every rank compares the full result with the oracle (test infrastructure).  gather="root": the blocks go
 to rank 0 only; rank 0 compares everything, the other ranks compare the rows they own and check that the
-rest of their matrix is empty."""
+rest of their matrix is empty.  gather="host": every rank copies its rows into one shared host mapping and
+every rank compares the full result."""
 import os
 import sys
 
@@ -29,13 +30,13 @@ for kind, n, kw in (("tet", 10, {}), ("mixed", 10, {"a": 2, "b": 5}), ("hex", 12
     mesh = meshgen.make_case(kind, n, **kw)
     I.load_mesh(mesh_obj=mesh)
     O = oracle.OracleInterpolator().load_mesh(mesh)
-    for gather in ("all", "root"):
+    for gather in ("all", "root", "host"):
         I.set_gather(gather)
         for method in ("idw", "ls", "gls"):
             W, nv = I.interpolate("u", method)
             Wo, nvo = O.interpolate("u", method)
             bounds = [int(b) for b in I.partition_bounds]
-            lo, hi = (0, W.shape[0]) if (gather == "all" or comm.rank == 0) else (bounds[comm.rank], bounds[comm.rank + 1])
+            lo, hi = (0, W.shape[0]) if (gather in ("all", "host") or comm.rank == 0) else (bounds[comm.rank], bounds[comm.rank + 1])
             ip, ix, dt = rows_of(W, lo, hi)
             ipo, ixo, dto = rows_of(Wo, lo, hi)
             same = W.shape == Wo.shape and np.array_equal(ip, ipo) and np.array_equal(ix, ixo)
