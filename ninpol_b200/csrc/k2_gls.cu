@@ -15,24 +15,31 @@
 //
 // Structure exploited: A is block sparse — 3 columns per element; an element row touches one block, the
 // 3 rows of an interior face touch the two blocks of its elements, a Neumann row touches one block.
-// The kernel runs a MULTIFRONTAL Householder QR per node: element blocks are eliminated in greedy
-// minimum-degree order (adjacency kept as per-lane bitmasks); eliminating block i gathers the row
-// groups that contain i into a small dense front (rows x (3*|blocks|+1)), applies 3 Householder
-// reflections, keeps the 3 pivot rows as rows of R and leaves the remaining rows as one new group.
+// The kernel runs a MULTIFRONTAL Householder QR per node, one warp per node, in three regimes:
+//  1. leaf fronts, one per LANE: blocks none of whose neighbours is eliminated yet have a front of original
+//     rows only (10 x (3 + 3 nn + 1), fixed sparsity); a greedy independent set of them is factored at
+//     once, lane b doing block b entirely in registers and writing its 3 rows of R and its 7-row
+//     contribution block straight to the slabs;
+//  2. general fronts, one per WARP: the remaining blocks go in greedy minimum-degree order (adjacency as
+//     per-lane bitmasks); the row groups containing the pivot are fetched into a dense front in shared
+//     memory (cp.async), the 3 pivot columns are factored with lanes over rows (registers + shuffles), the
+//     Householder vectors overwrite the panel columns of the front, and the three reflectors are applied
+//     to the other columns in two passes (lanes over columns; narrow fronts put several rows on the lanes);
+//  3. chained end game: a front's contribution block stays in place until the next pivot is known and the
+//     next front is built around it when that pivot is its first column and brings no new column — every
+//     step once the remaining blocks form a clique, i.e. the dense tall-skinny tail with most of the FLOPs.
 // An interior node of the 50M-tet mesh (E=24, F=36) costs ~0.11 MFLOP this way instead of 1.19 MFLOP
-// for a dense one-RHS QR (1.94 MFLOP in the reference).  Back substitution through the stored R rows
-// gives g, then r_i = 1 - d_i . g_i on the element rows.
+// for a dense one-RHS QR (1.94 MFLOP in the reference) and ~35 k warp-instructions.  Back substitution
+// through the stored R rows (leaf fronts again one per lane) gives g, then r_i = 1 - d_i . g_i.
 //
-// Mapping: one warp per node (one-warp CTAs, persistent, atomic work counter).  The dense front being
-// factored lives in shared memory (lanes over front columns, loops over front rows; the 3-column panel is
-// factored with lanes over rows in registers + shuffles); the row groups — original rows and the
-// contribution blocks left by earlier fronts — and the finished rows of R live in an append-only,
-// L2-resident global slab per CTA and are fetched into the front with cp.async (LDGSTS), so shared
-// memory holds only the hot data and ~10-27 nodes are resident per SM instead of 6.  Fronts taller than
-// the shared buffer are processed in row chunks (the 3 pivot rows of a chunk are carried into the next).
-// Nodes are bucketed into 7 size classes by star size; stars that do not fit (E > 64, a capacity
-// overflow detected at run time) go to the dense global-memory kernel of k2_gls_dense.cu.  The kernel is
-// latency / issue bound on this bookkeeping, not FP64 or HBM bound (profiles/).
+// Memory: the front being factored and small tables live in shared memory (17.6 KB for an interior tet
+// node); the row groups — original rows and contribution blocks — and the finished rows of R live in an
+// append-only, L2-resident global slab per CTA.  One-warp CTAs, persistent, atomic work counter; 12 CTAs
+// per SM for the interior-tet class (168 registers), 16 for smaller stars.  Fronts taller than the shared
+// buffer are processed in row chunks (the 3 pivot rows of a chunk are carried into the next).  Nodes are
+// bucketed into 7 size classes by star size; stars that do not fit (E > 64, a capacity overflow detected
+// at run time) go to the dense global-memory kernel of k2_gls_dense.cu.  The kernel is latency / issue
+// bound on this bookkeeping, not FP64 or HBM bound (profiles/).
 #include <stdlib.h>
 #include <string.h>
 #include "gls_common.cuh"

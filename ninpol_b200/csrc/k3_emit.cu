@@ -9,23 +9,35 @@
 // (SURVEY.md Q5).  Outputs are int32 indices / float64 data, the dtypes scipy picks.
 #include "common.cuh"
 
-// one warp per row: lanes stride over the row, ballot-compact the non-zeros
+// W lanes per row (W = 32, or 8 for meshes whose stars have <= 16 elements: four rows per warp): the lanes
+// stride over the row and ballot-compact the non-zeros
+template <int W>
 __global__ void __launch_bounds__(256)
 k_emit_rows(const int32_t *__restrict__ esup_ptr, const int32_t *__restrict__ esup, const double *__restrict__ wbuf,
             i64 wbase, const int32_t *__restrict__ indptr, i64 lo, i64 hi, int32_t *__restrict__ indices,
             double *__restrict__ data)
 {
-    i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
-    i64 p = lo + warp;
-    if (p >= hi) return;
-    int out0 = indptr[p];
-    int cnt = indptr[p + 1] - out0;
-    if (cnt == 0) return;
-    int b = esup_ptr[p], e = esup_ptr[p + 1];
+    const i64 gt = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & (W - 1);
+    const int shift = (threadIdx.x & 31) & ~(W - 1);          // first warp lane of this row's group
+    const unsigned gmask = (W == 32) ? 0xffffffffu : (((1u << W) - 1u) << shift);
+    i64 p = lo + gt / W;
+    const bool live = p < hi;                                  // whole groups are live or not; ballots need every lane
+    int out0 = 0, b = 0, e = 0;
+    if (live) {
+        out0 = indptr[p];
+        if (indptr[p + 1] != out0) {
+            b = esup_ptr[p];
+            e = esup_ptr[p + 1];
+        }
+    }
+    // all groups of a warp iterate together (the ballot is warp wide): up to the longest row of the warp
+    int len = e - b;
+#pragma unroll
+    for (int o = 16; o >= W; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
     int written = 0;
-    for (int q0 = b; q0 < e; q0 += 32) {
-        int q = q0 + lane;
+    for (int k0 = 0; k0 < len; k0 += W) {
+        int q = b + k0 + lane;
         double v = 0.0;
         int col = 0;
         if (q < e) {
@@ -33,9 +45,9 @@ k_emit_rows(const int32_t *__restrict__ esup_ptr, const int32_t *__restrict__ es
             col = esup[q];
         }
         bool keep = (q < e) && (v != 0.0);
-        unsigned m = __ballot_sync(0xffffffffu, keep);
+        unsigned m = __ballot_sync(0xffffffffu, keep) & gmask;
         if (keep) {
-            int pos = out0 + written + __popc(m & ((1u << lane) - 1u));
+            int pos = out0 + written + __popc(m & ((1u << (shift + lane)) - 1u));
             indices[pos] = col;
             data[pos] = v;
         }
@@ -47,9 +59,15 @@ int npb_k3_fill(npb_ctx *c, i64 lo, i64 hi)
 {
     if (hi <= lo) return NPB_OK;
     const int T = 256;
-    i64 threads = (hi - lo) * 32;
-    k_emit_rows<<<npb_blocks(threads, T), T, 0, c->stream>>>(c->esup_ptr, c->esup, c->wbuf, c->wbase, c->indptr, lo, hi,
-                                                            c->indices, c->data);
+    if (c->mx_epp <= 16) {
+        i64 threads = (hi - lo) * 8;
+        k_emit_rows<8><<<npb_blocks(threads, T), T, 0, c->stream>>>(c->esup_ptr, c->esup, c->wbuf, c->wbase, c->indptr, lo, hi,
+                                                                   c->indices, c->data);
+    } else {
+        i64 threads = (hi - lo) * 32;
+        k_emit_rows<32><<<npb_blocks(threads, T), T, 0, c->stream>>>(c->esup_ptr, c->esup, c->wbuf, c->wbase, c->indptr, lo, hi,
+                                                                    c->indices, c->data);
+    }
     NPB_LAUNCH(c);
     NPB_CUDA(cudaGetLastError());
     return NPB_OK;
