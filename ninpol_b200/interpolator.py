@@ -304,7 +304,8 @@ class Interpolator:
         cell_data = {}
         for variable in cell_data_dict:
             parts = [np.asarray(v) for t, v in cell_data_dict[variable].items() if t in self.types_per_dimension[dim]]
-            cell_data[variable] = np.concatenate(parts) if parts else np.zeros(0)
+            # one block of the mesh's dimension (the common case): no copy of the user's array
+            cell_data[variable] = parts[0] if len(parts) == 1 else (np.concatenate(parts) if parts else np.zeros(0))
             if variable == "permeability":
                 cell_data["diff_mag"] = self.compute_diffusion_magnitude(cell_data["permeability"])
         self.load_data(cell_data, "cells")
