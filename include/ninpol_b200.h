@@ -91,6 +91,13 @@ int npb_load_mesh(npb_ctx *ctx, int dim, int64_t n_elems, int64_t n_points, cons
                   const int64_t *element_types, const int64_t *npoel, const int64_t *nfael, const int64_t *lnofa,
                   const int64_t *lpofa, const int64_t *nedel, const int64_t *lpoed, const double *coords,
                   int build_edges);
+/* Same, with connectivity rows of conn_stride <= 8 nodes ([n_elems, conn_stride], no -1 padding needed up
+ * to the widest element type present): a one-block mesh (all tets, all hexes ...) passes its meshio block as
+ * it is and skips building and uploading the padded [n_elems, 8] array (3.2 GB at 50M cells). */
+int npb_load_mesh_strided(npb_ctx *ctx, int dim, int64_t n_elems, int64_t n_points, const int64_t *connectivity,
+                          int conn_stride, const int64_t *element_types, const int64_t *npoel, const int64_t *nfael,
+                          const int64_t *lnofa, const int64_t *lpofa, const int64_t *nedel, const int64_t *lpoed,
+                          const double *coords, int build_edges);
 
 /* Grid attributes (grid.pxd:128-187).  Scalars: dim n_elems n_points n_faces n_edges
  * MX_ELEMENTS_PER_POINT MX_POINTS_PER_POINT MX_ELEMENTS_PER_FACE MX_FACES_PER_POINT, and the flat

@@ -29,6 +29,8 @@ _SIGNATURES = {
     "npb_partition_elem_range": (ctypes.c_int, [ctypes.c_void_p, _c_i64p, _c_i64p]),
     "npb_set_cell_field_range": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64]),
     "npb_load_mesh": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64] + [ctypes.c_void_p] * 9 + [ctypes.c_int]),
+    "npb_load_mesh_strided": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int]
+                              + [ctypes.c_void_p] * 8 + [ctypes.c_int]),
     "npb_grid_scalar": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, _c_i64p]),
     "npb_grid_array": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64]),
     "npb_set_cell_field": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64]),
@@ -145,9 +147,14 @@ class Context:
     def load_mesh(self, dim, n_elems, n_points, conn, etype, npoel, nfael, lnofa, lpofa, nedel, lpoed, coords, build_edges):
         arrs = [np.ascontiguousarray(a, dtype=np.int64) for a in (conn, etype, npoel, nfael, lnofa, lpofa, nedel, lpoed)]
         coords = np.ascontiguousarray(coords, dtype=np.float64)
-        assert arrs[0].shape == (n_elems, 8) and coords.shape == (n_points, 3)
-        check(self.lib.npb_load_mesh(self.handle, int(dim), int(n_elems), int(n_points), *[_ptr(a) for a in arrs],
-                                     _ptr(coords), int(bool(build_edges))))
+        assert arrs[0].ndim == 2 and arrs[0].shape[0] == n_elems and 1 <= arrs[0].shape[1] <= 8 and coords.shape == (n_points, 3)
+        if arrs[0].shape[1] == 8:
+            check(self.lib.npb_load_mesh(self.handle, int(dim), int(n_elems), int(n_points), *[_ptr(a) for a in arrs],
+                                         _ptr(coords), int(bool(build_edges))))
+        else:   # a single-type block as meshio holds it: [n_elems, nodes per element], no padding
+            check(self.lib.npb_load_mesh_strided(self.handle, int(dim), int(n_elems), int(n_points), _ptr(arrs[0]),
+                                                 int(arrs[0].shape[1]), *[_ptr(a) for a in arrs[1:]], _ptr(coords),
+                                                 int(bool(build_edges))))
 
     def scalar(self, name):
         v = ctypes.c_int64(0)

@@ -350,6 +350,19 @@ extern "C" int npb_load_mesh(npb_ctx *c, int dim, int64_t n_elems, int64_t n_poi
                              const int64_t *lpofa, const int64_t *nedel, const int64_t *lpoed, const double *coords,
                              int build_edges)
 {
+    return npb_load_mesh_strided(c, dim, n_elems, n_points, conn, NPB_MX_PE, types, npoel, nfael, lnofa, lpofa, nedel,
+                                 lpoed, coords, build_edges);
+}
+
+extern "C" int npb_load_mesh_strided(npb_ctx *c, int dim, int64_t n_elems, int64_t n_points, const int64_t *conn,
+                                     int conn_stride, const int64_t *types, const int64_t *npoel, const int64_t *nfael,
+                                     const int64_t *lnofa, const int64_t *lpofa, const int64_t *nedel,
+                                     const int64_t *lpoed, const double *coords, int build_edges)
+{
+    if (conn_stride < 1 || conn_stride > NPB_MX_PE) {
+        npb_set_error("npb_load_mesh_strided: conn_stride must be in [1, %d]", NPB_MX_PE);
+        return NPB_ERR_ARG;
+    }
     if (!c || !conn || !types || !npoel || !nfael || !lnofa || !lpofa || !coords) {
         npb_set_error("npb_load_mesh: null argument");
         return NPB_ERR_ARG;
@@ -420,7 +433,11 @@ extern "C" int npb_load_mesh(npb_ctx *c, int dim, int64_t n_elems, int64_t n_poi
     }
     c->spe = mxp <= 4 ? 4 : 8;
     c->sfe = mxf <= 4 ? 4 : 6;
-    int rc = npb_k1_build(c, (const i64 *)conn, (const i64 *)types, coords);
+    if (mxp > conn_stride) {
+        npb_set_error("npb_load_mesh_strided: conn_stride %d is smaller than the %d nodes of an element type present", conn_stride, mxp);
+        return NPB_ERR_ARG;
+    }
+    int rc = npb_k1_build(c, (const i64 *)conn, conn_stride, (const i64 *)types, coords);
     if (rc != NPB_OK) {
         free_mesh(c);
         return rc;

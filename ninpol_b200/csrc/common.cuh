@@ -149,7 +149,7 @@ int npb_sort_pairs_u32(npb_ctx *c, const uint32_t *keys_in, uint32_t *keys_out, 
 int npb_propagate_heads(npb_ctx *c, uint2 *pairs, i64 n);
 
 // ---- kernels' host drivers ----
-int npb_k1_build(npb_ctx *c, const i64 *h_conn, const i64 *h_types, const double *h_coords);
+int npb_k1_build(npb_ctx *c, const i64 *h_conn, int conn_stride, const i64 *h_types, const double *h_coords);
 int npb_k1_geometry(npb_ctx *c);
 int npb_k1_extras(npb_ctx *c);  // psup, edges
 int npb_k2_idw_ls(npb_ctx *c, int method, i64 lo, i64 hi);

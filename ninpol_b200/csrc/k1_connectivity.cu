@@ -12,16 +12,16 @@
 #include "common.cuh"
 
 // ------------------------------------------------------------------------------------------------
-// int64 [n_elems, 8] (-1 padded) host layout  ->  int32 [n_elems, spe] + uint8 element types
+// int64 [n_elems, cstride] (-1 padded) host layout  ->  int32 [n_elems, spe] + uint8 element types
 // ------------------------------------------------------------------------------------------------
-__global__ void k_convert_conn(const i64 *__restrict__ conn, const i64 *__restrict__ types, i64 n_elems, int spe,
+__global__ void k_convert_conn(const i64 *__restrict__ conn, int cstride, const i64 *__restrict__ types, i64 n_elems, int spe,
                                int32_t *__restrict__ inpoel, uint8_t *__restrict__ etype)
 {
     i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_elems * spe) return;
     i64 e = idx / spe;
     int j = (int)(idx - e * spe);
-    inpoel[idx] = (int32_t)conn[e * NPB_MX_PE + j];
+    inpoel[idx] = j < cstride ? (int32_t)conn[e * cstride + j] : -1;
     if (j == 0) etype[e] = (uint8_t)types[e];
 }
 
@@ -238,7 +238,7 @@ __global__ void k_fill_fsup(const int32_t *__restrict__ inpofa, i64 n_faces, con
 // ------------------------------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------------------------------
-int npb_k1_build(npb_ctx *c, const i64 *h_conn, const i64 *h_types, const double *h_coords)
+int npb_k1_build(npb_ctx *c, const i64 *h_conn, int cstride, const i64 *h_types, const double *h_coords)
 {
     const int T = 256;
     cudaStream_t s = c->stream;
@@ -249,15 +249,15 @@ int npb_k1_build(npb_ctx *c, const i64 *h_conn, const i64 *h_types, const double
     {
         NpbTimer tm(c, "h2d_mesh");
         i64 *d_conn = nullptr, *d_types = nullptr;
-        NPB_CUDA(cudaMalloc(&d_conn, sizeof(i64) * ne * NPB_MX_PE));
+        NPB_CUDA(cudaMalloc(&d_conn, sizeof(i64) * ne * cstride));
         NPB_CUDA(cudaMalloc(&d_types, sizeof(i64) * ne));
-        NPB_TRY(npb_h2d(c, d_conn, h_conn, sizeof(i64) * ne * NPB_MX_PE));
+        NPB_TRY(npb_h2d(c, d_conn, h_conn, sizeof(i64) * ne * cstride));
         NPB_TRY(npb_h2d(c, d_types, h_types, sizeof(i64) * ne));
         NPB_TRY(npb_alloc(c, (void **)&c->inpoel, sizeof(int32_t) * ne * spe));
         NPB_TRY(npb_alloc(c, (void **)&c->etype, ne));
         NPB_TRY(npb_alloc(c, (void **)&c->coords, sizeof(double) * np * 3));
         NPB_TRY(npb_h2d(c, c->coords, h_coords, sizeof(double) * np * 3));
-        k_convert_conn<<<npb_blocks(ne * spe, T), T, 0, s>>>(d_conn, d_types, ne, spe, c->inpoel, c->etype);
+        k_convert_conn<<<npb_blocks(ne * spe, T), T, 0, s>>>(d_conn, cstride, d_types, ne, spe, c->inpoel, c->etype);
         NPB_LAUNCH(c);
         tm.stop();
         NPB_CUDA(cudaStreamSynchronize(s));

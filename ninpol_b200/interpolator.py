@@ -189,8 +189,10 @@ class Interpolator:
             else:
                 self.logger.log("Using mesh object")
                 self.mesh_obj = mesh_obj
-            args = self.process_mesh(self.mesh_obj)
-            self.points_coords = np.asarray(self.mesh_obj.points).astype(DTYPE_F)
+            # a mesh file is cached with the reference's padded [n_elems, 8] table (make_cache); a mesh object
+            # with a single cell block of the mesh's dimension goes to the device as it is
+            args = self.process_mesh(self.mesh_obj, padded=(filename != ""))
+            self.points_coords = np.asarray(self.mesh_obj.points, dtype=DTYPE_F)
         dim, n_elems, n_points, npoel, nfael, lnofa, lpofa, nedel, lpoed, connectivity, element_types = args[:11]
         coords = np.asarray(self.points_coords, dtype=DTYPE_F)
         if coords.shape[1] != 3:
@@ -251,7 +253,10 @@ class Interpolator:
     # ------------------------------------------------------------------------------------------
     # process_mesh (interpolator.pyx:255-369), vectorised
     # ------------------------------------------------------------------------------------------
-    def process_mesh(self, mesh):
+    def process_mesh(self, mesh, padded=True):
+        """Same tuple as the reference's process_mesh.  padded=False (internal): a mesh with ONE cell block of
+        its dimension keeps that block's [n_elems, nodes-per-element] array instead of the -1 padded
+        [n_elems, 8] copy (npb_load_mesh_strided takes it as it is)."""
         dim = 1
         for blk in mesh.cells:
             for dimension, names in self.types_per_dimension.items():
@@ -261,6 +266,10 @@ class Interpolator:
         blocks = [b for b in mesh.cells if b.type in self.types_per_dimension[dim]]
         n_elems = int(sum(len(b.data) for b in blocks))
         n_points = int(np.asarray(mesh.points).shape[0])
+        if not padded and len(blocks) == 1 and np.asarray(blocks[0].data).ndim == 2 and n_elems > 0:
+            connectivity = np.ascontiguousarray(blocks[0].data, dtype=DTYPE_I)
+            element_types = np.full(n_elems, self.point_ordering["elements"][blocks[0].type]["element_type"], dtype=DTYPE_I)
+            return (dim, n_elems, n_points) + tuple(tables) + (connectivity, element_types, self.logging, self.build_edges)
         connectivity = -np.ones((n_elems, et.MAX_POINTS_PER_ELEMENT), dtype=DTYPE_I)
         element_types = -np.ones(n_elems, dtype=DTYPE_I)
         at = 0
