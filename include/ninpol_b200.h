@@ -137,6 +137,14 @@ int npb_set_point_flags_f64(npb_ctx *ctx, const double *neumann_flag, int64_t n_
 int npb_interpolate_count(npb_ctx *ctx, int method, int64_t *nnz);
 int npb_interpolate_fetch(npb_ctx *ctx, int32_t *indptr, int32_t *indices, double *data, double *neumann);
 
+/* The plug-in's own output, for callers that sit where Interpolator.prepare_interpolator sits
+ * (interpolator.pyx:631-670): dense weights [n_points, MX_ELEMENTS_PER_POINT] (row stride
+ * MX_ELEMENTS_PER_POINT, column k of row p <-> esup[esup_ptr[p] + k], untouched entries 0) and neumann_ws
+ * [n_points], exactly the two caller-allocated outputs of `XInterpolation.prepare(grid, cells_data,
+ * points_data, faces_data, variable_to_index, variable, target_points, weights, neumann_ws)`
+ * (idw.pxd:19-24, ls.pxd:20-25, gls.pxd:22-27), target_points = all nodes.  Single GPU. */
+int npb_interpolate_dense(npb_ctx *ctx, int method, double *weights, double *neumann_ws);
+
 /* The same result as npb_interpolate_count + npb_interpolate_fetch, computed as a pipeline over n_chunks
  * contiguous node chunks on one GPU: the cell-field slice of chunk k+1 is uploaded and the CSR block of
  * chunk k-1 is downloaded while chunk k computes (three CUDA streams).  perm_host / diff_mag_host: the

@@ -38,6 +38,7 @@ _SIGNATURES = {
     "npb_set_point_flags_f64": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]),
     "npb_interpolate_count": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_i64p]),
     "npb_interpolate_fetch": (ctypes.c_int, [ctypes.c_void_p] * 5),
+    "npb_interpolate_dense": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "npb_interpolate_streamed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 6 + [ctypes.c_int64, _c_i64p]),
     "npb_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]),
     "npb_launch_count": (ctypes.c_int, [ctypes.c_void_p, _c_i64p]),
@@ -197,6 +198,12 @@ class Context:
                                                 _ptr(indptr), _ptr(indices), _ptr(data), _ptr(neumann),
                                                 int(min(indices.size, data.size)), ctypes.byref(nnz)))
         return int(nnz.value)
+
+    def interpolate_dense(self, method, weights, neumann_ws):
+        """The plug-in's dense outputs (weights [n_points, MX_ELEMENTS_PER_POINT], neumann_ws [n_points])."""
+        assert weights.flags.c_contiguous and neumann_ws.flags.c_contiguous
+        assert weights.dtype == np.float64 and neumann_ws.dtype == np.float64
+        check(self.lib.npb_interpolate_dense(self.handle, METHOD_IDS[method], _ptr(weights), _ptr(neumann_ws)))
 
     def interpolate_count(self, method):
         nnz = ctypes.c_int64(0)

@@ -35,11 +35,31 @@ UNITS = {
 }
 
 
-def _stale(target, deps):
-    if not os.path.exists(target):
+def _digest(paths, extra=()):
+    """Content hash of the inputs of one build step.  Staleness is decided on content, not on mtimes: the
+    gpurun snapshot does not preserve them, and a stale binary must never be tested against edited sources."""
+    import hashlib
+    h = hashlib.sha256()
+    for p in sorted(paths):
+        h.update(os.path.basename(p).encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    for e in extra:
+        h.update(str(e).encode())
+    return h.hexdigest()
+
+
+def _stale(target, stamp_value):
+    stamp = target + ".sha"
+    if not os.path.exists(target) or not os.path.exists(stamp):
         return True
-    t = os.path.getmtime(target)
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(stamp) as f:
+        return f.read().strip() != stamp_value
+
+
+def _mark(target, stamp_value):
+    with open(target + ".sha", "w") as f:
+        f.write(stamp_value)
 
 
 def build(force=False, verbose=False):
@@ -48,12 +68,16 @@ def build(force=False, verbose=False):
     headers.append(os.path.join(HERE, "..", "include", "ninpol_b200.h"))
     jobs = []
     objs = []
+    stamps = []
     for src, extra in UNITS.items():
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
         objs.append(o)
-        if force or _stale(o, [s] + headers):
-            jobs.append([NVCC] + ARCH + COMMON + extra + EXTRA + ["-c", s, "-o", o])
+        cmd = [NVCC] + ARCH + COMMON + extra + EXTRA + ["-c", s, "-o", o]
+        stamp = _digest([s] + headers, cmd)
+        stamps.append(stamp)
+        if force or _stale(o, stamp):
+            jobs.append((cmd, o, stamp))
 
     def run(cmd):
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
@@ -62,11 +86,30 @@ def build(force=False, verbose=False):
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for " + cmd[-3])
 
+    def compile_one(job):
+        cmd, o, stamp = job
+        run(cmd)
+        _mark(o, stamp)
+
     with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
-        list(ex.map(run, jobs))
-    if jobs or force or _stale(LIB, objs):
+        list(ex.map(compile_one, jobs))
+    lib_stamp = _digest([], stamps)
+    if jobs or force or _stale(LIB, lib_stamp):
         run([NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-ldl", "-lpthread", "-ccbin", "/usr/bin/g++"])
+        _mark(LIB, lib_stamp)
     return LIB
+
+
+def is_current():
+    """True when libninpol_b200.so was built from exactly the sources in the tree."""
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(HERE, "..", "include", "ninpol_b200.h"))
+    stamps = []
+    for src, extra in UNITS.items():
+        s = os.path.join(CSRC, src)
+        o = os.path.join(OBJ, src.replace(".cu", ".o"))
+        stamps.append(_digest([s] + headers, [NVCC] + ARCH + COMMON + extra + EXTRA + ["-c", s, "-o", o]))
+    return not _stale(LIB, _digest([], stamps))
 
 
 if __name__ == "__main__":

@@ -66,6 +66,11 @@ NpbTimer::NpbTimer(npb_ctx *c_, const char *n, bool accumulate_) : c(c_), name(n
     cudaEventCreate(&b);
     cudaEventRecord(a, c->stream);
 }
+NpbTimer::~NpbTimer()
+{
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+}
 void NpbTimer::stop()
 {
     if (!a) return;
@@ -225,11 +230,22 @@ extern "C" int npb_create(int device, npb_ctx **out)
     npb_ctx *c = new npb_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    NPB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    NPB_CUDA(cudaMalloc(&c->counters, sizeof(int) * 64));
-    NPB_CUDA(cudaMemset(c->counters, 0, sizeof(int) * 64));
-    NPB_CUDA(cudaHostAlloc((void **)&c->h_small, sizeof(int) * 64, cudaHostAllocMapped));
-    NPB_CUDA(cudaHostGetDevicePointer((void **)&c->d_small, c->h_small, 0));
+    auto init = [&]() -> int {
+        NPB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        NPB_CUDA(cudaMalloc(&c->counters, sizeof(int) * 128));
+        NPB_CUDA(cudaMemset(c->counters, 0, sizeof(int) * 128));
+        NPB_CUDA(cudaHostAlloc((void **)&c->h_small, sizeof(int) * 64, cudaHostAllocMapped));
+        NPB_CUDA(cudaHostGetDevicePointer((void **)&c->d_small, c->h_small, 0));
+        return NPB_OK;
+    };
+    int rc = init();
+    if (rc != NPB_OK) {   // nothing half-built survives a failed create
+        if (c->h_small) cudaFreeHost(c->h_small);
+        if (c->counters) cudaFree(c->counters);
+        if (c->stream) cudaStreamDestroy(c->stream);
+        delete c;
+        return rc;
+    }
     *out = c;
     return NPB_OK;
 }
@@ -433,6 +449,20 @@ extern "C" int npb_load_mesh_strided(npb_ctx *c, int dim, int64_t n_elems, int64
     }
     c->spe = mxp <= 4 ? 4 : 8;
     c->sfe = mxf <= 4 ? 4 : 6;
+    {   // the device indexes fsup / esuf / inpofa with int32 as well: bound their flat lengths by the present types
+        int64_t fn = 0;   // max over present types of sum_f lnofa[t][f] (node incidences of an element's faces)
+        for (int t = 0; t < NPB_N_TYPES; t++) {
+            if (!present[t]) continue;
+            int64_t sum = 0;
+            for (int f = 0; f < c->tab.nfael[t]; f++) sum += c->tab.lnofa[t][f];
+            if (sum > fn) fn = sum;
+        }
+        if (n_elems * fn >= (1ll << 31) || n_elems * (int64_t)mxf * NPB_MX_PF >= (1ll << 31)) {
+            npb_set_error("mesh too large for 32-bit device ids: up to %lld node->face incidences (n_elems=%lld)",
+                          (long long)(n_elems * fn), (long long)n_elems);
+            return NPB_ERR_RANGE;
+        }
+    }
     if (mxp > conn_stride) {
         npb_set_error("npb_load_mesh_strided: conn_stride %d is smaller than the %d nodes of an element type present", conn_stride, mxp);
         return NPB_ERR_ARG;
@@ -792,6 +822,72 @@ extern "C" int npb_interpolate_fetch(npb_ctx *c, int32_t *indptr, int32_t *indic
         if (neumann) NPB_TRY(npb_d2h(c, neumann, c->neumann, sizeof(double) * c->n_points));
         tm.stop();
     }
+    NPB_CUDA(cudaStreamSynchronize(s));
+    return NPB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plug-in contract: dense weights[n_points, MX_ELEMENTS_PER_POINT] + neumann_ws, as XInterpolation.prepare
+// leaves them (idw.pxd:19-24, ls.pxd:20-25, gls.pxd:22-27; caller-allocated, interpolator.pyx:645-651)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_dense_rows(const int32_t *__restrict__ esup_ptr, const double *__restrict__ wbuf, i64 wbase,
+                             const double *__restrict__ neumann, i64 n_points, int mx, double *__restrict__ out)
+{
+    i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_points * mx) return;
+    i64 p = idx / mx;
+    int k = (int)(idx - p * mx);
+    int b = esup_ptr[p], e = esup_ptr[p + 1];
+    // wbuf holds the CSR value w + neumann_ws (interpolator.pyx:618); the plug-in's own output is w.  IDW / LS
+    // never write neumann_ws (it is +0.0), so this is exact for them; for GLS it is w to within one rounding
+    out[idx] = (k < e - b) ? wbuf[(i64)b + k - wbase] - neumann[p] : 0.0;
+}
+
+extern "C" int npb_interpolate_dense(npb_ctx *c, int method, double *weights, double *neumann_ws)
+{
+    if (!c || !weights || !neumann_ws) return NPB_ERR_ARG;
+    if (!c->mesh_loaded) {
+        npb_set_error("Grid not initialized. Please load a mesh first.");
+        return NPB_ERR_STATE;
+    }
+    if (method != NPB_METHOD_IDW && method != NPB_METHOD_LS && method != NPB_METHOD_GLS) {
+        npb_set_error("unknown method id %d", method);
+        return NPB_ERR_ARG;
+    }
+    if (c->world != 1) {
+        npb_set_error("npb_interpolate_dense: the dense plug-in view is single-GPU only");
+        return NPB_ERR_STATE;
+    }
+    if (!c->have_flags) {
+        npb_set_error("neumann flags have not been set");
+        return NPB_ERR_STATE;
+    }
+    if (method == NPB_METHOD_GLS && (!c->have_perm || !c->have_dm)) {
+        npb_set_error("GLS needs the 'permeability' and 'diff_mag' cell fields");
+        return NPB_ERR_STATE;
+    }
+    NPB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    c->counted = false;
+    c->filled = false;
+    NPB_TRY(npb_ensure((void **)&c->wbuf, &c->wbuf_cap, sizeof(double) * (size_t)(c->wlen > 0 ? c->wlen : 1)));
+    if (method == NPB_METHOD_GLS)
+        NPB_TRY(npb_k2_gls(c, c->lo, c->hi));
+    else {
+        int used = 0;
+        NPB_TRY(npb_k2_idw_ls_tiles(c, method, c->lo, c->hi, &used));
+        if (!used) NPB_TRY(npb_k2_idw_ls(c, method, c->lo, c->hi));
+    }
+    const i64 total = c->n_points * (i64)c->mx_epp;
+    NpbTmp dense;
+    NPB_CUDA(dense.alloc(sizeof(double) * (size_t)total));
+    if (total > 0) {
+        k_dense_rows<<<npb_blocks(total, 256), 256, 0, s>>>(c->esup_ptr, c->wbuf, c->wbase, c->neumann, c->n_points, c->mx_epp,
+                                                            dense.as<double>());
+        NPB_LAUNCH(c);
+        NPB_TRY(npb_d2h(c, weights, dense.p, sizeof(double) * (size_t)total));
+    }
+    NPB_TRY(npb_d2h(c, neumann_ws, c->neumann, sizeof(double) * (size_t)c->n_points));
     NPB_CUDA(cudaStreamSynchronize(s));
     return NPB_OK;
 }

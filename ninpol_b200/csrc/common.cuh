@@ -138,6 +138,9 @@ struct NpbTimer {
     cudaEvent_t a, b;
     bool accumulate;
     NpbTimer(npb_ctx *c_, const char *n, bool accumulate_ = false);   // accumulate: add to timings[name]
+    ~NpbTimer();   // an early (error) return must not leak the two events
+    NpbTimer(const NpbTimer &) = delete;
+    NpbTimer &operator=(const NpbTimer &) = delete;
     void stop();
 };
 
@@ -163,6 +166,16 @@ int npb_minmax_i32(npb_ctx *c, const int32_t *in, i64 n, int32_t *h_min, int32_t
 int npb_k4_gather_counts(npb_ctx *c);
 int npb_k4_gather_blocks(npb_ctx *c);
 int npb_export_array(npb_ctx *c, const char *name, void *out, i64 cap);
+// cudaMalloc'ed temporary that is freed when it goes out of scope (error returns included)
+struct NpbTmp {
+    void *p = nullptr;
+    ~NpbTmp() { if (p) cudaFree(p); }
+    NpbTmp() = default;
+    NpbTmp(const NpbTmp &) = delete;
+    NpbTmp &operator=(const NpbTmp &) = delete;
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 8); }
+    template <class T> T *as() { return (T *)p; }
+};
 
 static inline unsigned npb_blocks(i64 n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 #define NPB_LAUNCH(c) ((c)->launches++)

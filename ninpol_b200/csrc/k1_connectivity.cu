@@ -14,15 +14,28 @@
 // ------------------------------------------------------------------------------------------------
 // int64 [n_elems, cstride] (-1 padded) host layout  ->  int32 [n_elems, spe] + uint8 element types
 // ------------------------------------------------------------------------------------------------
+// Node ids are validated here, before anything scatters through them: the first npoel[type] ids of an element
+// must lie in [0, n_points) (a 1-based or mis-indexed mesh would otherwise write out of bounds on the device;
+// the reference segfaults on the host).  bad[0] = lowest offending element id + 1 (0: none).
 __global__ void k_convert_conn(const i64 *__restrict__ conn, int cstride, const i64 *__restrict__ types, i64 n_elems, int spe,
-                               int32_t *__restrict__ inpoel, uint8_t *__restrict__ etype)
+                               ElemTables tab, i64 n_points, int32_t *__restrict__ inpoel, uint8_t *__restrict__ etype,
+                               unsigned long long *__restrict__ bad)
 {
     i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_elems * spe) return;
     i64 e = idx / spe;
     int j = (int)(idx - e * spe);
-    inpoel[idx] = j < cstride ? (int32_t)conn[e * cstride + j] : -1;
-    if (j == 0) etype[e] = (uint8_t)types[e];
+    int t = (int)types[e];
+    i64 v = j < cstride ? conn[e * cstride + j] : -1;
+    if (j < tab.npoel[t]) {
+        if (v < 0 || v >= n_points) {
+            atomicMin(bad, (unsigned long long)e);
+            v = 0;   // keep the table in range; the build is abandoned below
+        }
+    } else
+        v = -1;      // slots past the element's node count are padding whatever the caller left there
+    inpoel[idx] = (int32_t)v;
+    if (j == 0) etype[e] = (uint8_t)t;
 }
 
 // histogram of node incidences over the padded (element, local node) table
@@ -248,21 +261,28 @@ int npb_k1_build(npb_ctx *c, const i64 *h_conn, int cstride, const i64 *h_types,
     // ---- H2D of the reference-layout inputs, then compaction to int32 on the device ----
     {
         NpbTimer tm(c, "h2d_mesh");
-        i64 *d_conn = nullptr, *d_types = nullptr;
-        NPB_CUDA(cudaMalloc(&d_conn, sizeof(i64) * ne * cstride));
-        NPB_CUDA(cudaMalloc(&d_types, sizeof(i64) * ne));
+        NpbTmp t_conn, t_types;
+        NPB_CUDA(t_conn.alloc(sizeof(i64) * ne * cstride));
+        NPB_CUDA(t_types.alloc(sizeof(i64) * ne));
+        i64 *d_conn = t_conn.as<i64>(), *d_types = t_types.as<i64>();
         NPB_TRY(npb_h2d(c, d_conn, h_conn, sizeof(i64) * ne * cstride));
         NPB_TRY(npb_h2d(c, d_types, h_types, sizeof(i64) * ne));
         NPB_TRY(npb_alloc(c, (void **)&c->inpoel, sizeof(int32_t) * ne * spe));
         NPB_TRY(npb_alloc(c, (void **)&c->etype, ne));
         NPB_TRY(npb_alloc(c, (void **)&c->coords, sizeof(double) * np * 3));
         NPB_TRY(npb_h2d(c, c->coords, h_coords, sizeof(double) * np * 3));
-        k_convert_conn<<<npb_blocks(ne * spe, T), T, 0, s>>>(d_conn, cstride, d_types, ne, spe, c->inpoel, c->etype);
+        unsigned long long *d_bad = (unsigned long long *)(c->counters + 64);   // 8-byte aligned slot of the 128-int counter block
+        NPB_CUDA(cudaMemsetAsync(d_bad, 0xff, sizeof(unsigned long long), s));
+        k_convert_conn<<<npb_blocks(ne * spe, T), T, 0, s>>>(d_conn, cstride, d_types, ne, spe, c->tab, np, c->inpoel, c->etype, d_bad);
         NPB_LAUNCH(c);
         tm.stop();
+        unsigned long long h_bad = 0;
+        NPB_CUDA(cudaMemcpyAsync(&h_bad, d_bad, sizeof(h_bad), cudaMemcpyDeviceToHost, s));
         NPB_CUDA(cudaStreamSynchronize(s));
-        NPB_CUDA(cudaFree(d_conn));
-        NPB_CUDA(cudaFree(d_types));
+        if (h_bad != ~0ull) {
+            npb_set_error("element %llu has a node id outside [0, %lld) among its first npoel[type] entries", h_bad, (long long)np);
+            return NPB_ERR_ARG;
+        }
     }
     // Device time of K1 = sum of the kernel segments below; cudaMalloc / host round trips for the sizes
     // (n_faces, row totals) sit between the segments and are not counted.
@@ -271,14 +291,15 @@ int npb_k1_build(npb_ctx *c, const i64 *h_conn, int cstride, const i64 *h_types,
     NPB_CUDA(cudaMemsetAsync(d_mx, 0, sizeof(int) * 8, s));
 
     // ---- esup ----
-    int32_t *cursor = nullptr, *fbase = nullptr;
+    NpbTmp t_cursor, t_fbase;
     NPB_TRY(npb_alloc(c, (void **)&c->esup_ptr, sizeof(int32_t) * (np + 1)));
     NPB_TRY(npb_alloc(c, (void **)&c->esuel, sizeof(int32_t) * ne * sfe));
     NPB_TRY(npb_alloc(c, (void **)&c->infael, sizeof(int32_t) * ne * sfe));
     NPB_TRY(npb_alloc(c, (void **)&c->bpoint, (size_t)np));
     NPB_TRY(npb_alloc(c, (void **)&c->fsup_ptr, sizeof(int32_t) * (np + 1)));
-    NPB_CUDA(cudaMalloc(&cursor, sizeof(int32_t) * (np + 1)));
-    NPB_CUDA(cudaMalloc(&fbase, sizeof(int32_t) * (ne + 1)));
+    NPB_CUDA(t_cursor.alloc(sizeof(int32_t) * (np + 1)));
+    NPB_CUDA(t_fbase.alloc(sizeof(int32_t) * (ne + 1)));
+    int32_t *cursor = t_cursor.as<int32_t>(), *fbase = t_fbase.as<int32_t>();
     {
         NpbTimer tm(c, "k1_esup", true);
         NPB_CUDA(cudaMemsetAsync(c->esup_ptr, 0, sizeof(int32_t) * (np + 1), s));
@@ -381,8 +402,6 @@ int npb_k1_build(npb_ctx *c, const i64 *h_conn, int cstride, const i64 *h_types,
     // esuf rows are [owner] or [owner, other] (grid.pyx:390-416)
     c->len_esuf = 2 * c->n_faces - h_mx[2];
     c->mx_epf = c->n_faces == 0 ? 0 : (h_mx[2] < c->n_faces ? 2 : 1);
-    NPB_CUDA(cudaFree(cursor));
-    NPB_CUDA(cudaFree(fbase));
     // ---- geometry (k1_geometry.cu, compiled without FMA contraction) ----
     NPB_TRY(npb_k1_geometry(c));
     for (const char *k : {"k1_esup", "k1_esuel", "k1_faces", "k1_fsup", "k1_geom"}) c->timings["k1"] += c->timings[k];

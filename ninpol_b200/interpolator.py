@@ -57,17 +57,21 @@ class _Method:
         if grid is not I.grid:
             raise ValueError("this plug-in is bound to its Interpolator's grid")
         I._check_targets(target_points)
+        n, mx = grid.n_points, grid.MX_ELEMENTS_PER_POINT
+        w = np.asarray(weights)
+        nw = np.asarray(neumann_ws)
+        if w.shape != (n, mx) or nw.shape != (n,) or w.dtype != DTYPE_F or nw.dtype != DTYPE_F:
+            raise ValueError(f"weights must be float64 [{n}, {mx}] and neumann_ws float64 [{n}] (interpolator.pyx:645-651)")
         I._stage_inputs(self.method, variable, variable_to_index, cells_data, points_data)
-        indptr, indices, data, neumann = I._run(self.method)
-        # CSR rows hold w + neumann_ws (interpolator.pyx:618); the plug-in contract is w itself
-        esup_ptr, esup = np.asarray(grid.esup_ptr), np.asarray(grid.esup)
-        rows = np.repeat(np.arange(grid.n_points, dtype=np.int64), np.diff(indptr))
-        # position of every kept entry inside its (ascending) esup row
-        stride = grid.n_elems + 1
-        allkey = np.repeat(np.arange(grid.n_points, dtype=np.int64), np.diff(esup_ptr)) * stride + esup
-        pos = np.searchsorted(allkey, rows * stride + indices) - esup_ptr[rows]
-        weights[rows, pos] = data - neumann[rows]
-        neumann_ws[:] = neumann
+        # the kernels' esup-indexed values go straight into the caller's dense rows (npb_interpolate_dense):
+        # nothing is rebuilt from the zero-eliminated CSR
+        wc = w if w.flags.c_contiguous else np.empty((n, mx), dtype=DTYPE_F)
+        nc = nw if nw.flags.c_contiguous else np.empty(n, dtype=DTYPE_F)
+        I._ctx.interpolate_dense(self.method, wc, nc)
+        if wc is not w:
+            w[...] = wc
+        if nc is not nw:
+            nw[...] = nc
 
     __call__ = prepare
 

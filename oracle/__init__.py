@@ -11,7 +11,7 @@ Contents
   build_ref.py      recipe that compiles the unmodified reference into oracle/_ref/ (git-ignored).
   load_reference()  imports that compiled reference (with the meshio shim on sys.path).
 
-Parity status: pinned against the compiled reference (tests/test_oracle_vs_reference.py) and the
+Parity status: pinned against the compiled reference (tests/test_oracle.py) and the
 fixtures under tests/golden/.
 """
 import ctypes
@@ -316,6 +316,60 @@ class OracleInterpolator:
         W = sp.csr_matrix((data, (rows, esup.copy())), shape=(g.n_points, g.n_elems))
         W.eliminate_zeros()
         return W, nws
+
+
+def sample_rows(grid, method, nodes, flags, permeability=None, diff_mag=None, neumann_val=None):
+    """The reference's per-node loops (idw.pyx:57-84, ls.pyx:56-135, gls.pyx:161-219) over a SAMPLE of target
+    nodes.  `grid` is anything with the reference's Grid attributes in the reference's layouts (an
+    OracleGrid, or the arrays exported by the CUDA path — the at-size parity tests use that: the connectivity
+    arrays are checked separately, and a node's weights depend only on its own esup / fsup rows).
+    Returns dense weights [len(nodes), MX_ELEMENTS_PER_POINT] and neumann_ws [len(nodes)]."""
+    L = lib()
+    i8 = lambda a: np.ascontiguousarray(a, dtype=np.int64)
+    f8 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    nodes = i8(nodes)
+    ncol = int(grid.MX_ELEMENTS_PER_POINT)
+    weights = np.zeros((len(nodes), ncol), dtype=np.float64)
+    nws = np.zeros(len(nodes), dtype=np.float64)
+    esup_ptr, esup, bp, fl = i8(grid.esup_ptr), i8(grid.esup), i8(grid.boundary_points), i8(flags)
+    coords, cent = f8(grid.point_coords), f8(grid.centroids)
+    if method == "idw":
+        L.orc_idw_nodes(_ll(grid.dim), _ll(len(nodes)), _p(nodes), _ll(ncol), _p(esup_ptr), _p(esup), _p(bp), _p(fl),
+                        _p(coords), _p(cent), _p(weights))
+    elif method == "ls":
+        L.orc_ls_nodes(_ll(len(nodes)), _p(nodes), _ll(ncol), _p(esup_ptr), _p(esup), _p(bp), _p(fl), _p(coords), _p(cent),
+                       _p(weights))
+    elif method == "gls":
+        L.orc_gls_nodes.restype = ctypes.c_int
+        fsup_ptr, fsup, esuf_ptr, esuf = i8(grid.fsup_ptr), i8(grid.fsup), i8(grid.esuf_ptr), i8(grid.esuf)
+        inpofa, bf = i8(grid.inpofa), i8(grid.boundary_faces)
+        fcent, fnorm = f8(grid.faces_centers), f8(grid.normal_faces)
+        perm = f8(np.reshape(permeability, (-1, 9)))
+        dm = f8(diff_mag)
+        nval = f8(neumann_val) if neumann_val is not None else np.zeros(grid.n_points)
+        dgels, dgemv = _blas_lapack_pointers()
+        rc = L.orc_gls_nodes(_ll(len(nodes)), _p(nodes), _ll(ncol), _ll(grid.MX_FACES_PER_POINT), _p(esup_ptr), _p(esup),
+                             _p(fsup_ptr), _p(fsup), _p(esuf_ptr), _p(esuf), _p(inpofa), _p(bf), _p(bp), _p(fl), _p(nval),
+                             _p(coords), _p(cent), _p(fcent), _p(fnorm), _p(perm), _p(dm), dgels, dgemv, _p(weights), _p(nws),
+                             _ll(-1), None, None)
+        if rc != 0:
+            raise MemoryError("oracle gls")
+    else:
+        raise ValueError(method)
+    return weights, nws
+
+
+def sample_csr_rows(grid, nodes, weights, nws):
+    """interpolator.pyx:598-624 for the sampled rows: data = weights + neumann_ws in esup order, exact zeros
+    dropped.  Returns a list of (indices int64, data float64) per sampled node."""
+    esup_ptr, esup = np.asarray(grid.esup_ptr), np.asarray(grid.esup)
+    out = []
+    for i, p in enumerate(np.asarray(nodes)):
+        b, e = int(esup_ptr[p]), int(esup_ptr[p + 1])
+        d = weights[i, :e - b] + nws[i]
+        keep = d != 0.0
+        out.append((np.asarray(esup[b:e])[keep].astype(np.int64), d[keep]))
+    return out
 
 
 def load_reference():

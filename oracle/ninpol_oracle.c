@@ -10,7 +10,7 @@
  * follows is cited at the function.  Arrays use the reference's own dtypes and layouts (int64 ids,
  * -1 padding, float64 geometry) so results compare with np.array_equal.
  *
- * Parity status: PINNED.  tests/test_oracle_vs_reference.py compares every output of this file with
+ * Parity status: PINNED.  tests/test_oracle.py compares every output of this file with
  * the compiled reference (oracle/_ref, built by oracle/build_ref.py) on tet / hex / mixed meshes, and
  * tests/golden/ holds fixtures generated from that compiled reference (tests/golden/make_golden.py).
  *
@@ -357,11 +357,17 @@ void orc_normals(i64 dim, i64 n_faces, const i64 *inpofa, const double *coords, 
  * IDWInterpolation.inverse_distance — idw.pyx:35-84, all nodes as targets.  weights is
  * [n_points, ncol] zero-initialised (interpolator.pyx:650).
  * ---------------------------------------------------------------------------------------------- */
-void orc_idw(i64 dim, i64 n_points, i64 ncol, const i64 *esup_ptr, const i64 *esup, const i64 *boundary_points,
-             const i64 *neumann_point, const double *coords, const double *centroids, double *weights)
+/* `list` (n_list node ids) restricts the loop to a sample of target nodes — the reference's
+ * `target_points` loop variable (idw.pyx:57-60) — and row i of `weights` then belongs to list[i];
+ * list == NULL means every node, row = node id. */
+void orc_idw_nodes(i64 dim, i64 n_list, const i64 *list, i64 ncol, const i64 *esup_ptr, const i64 *esup,
+                   const i64 *boundary_points, const i64 *neumann_point, const double *coords, const double *centroids,
+                   double *weights_out)
 {
     const float machine_epsilon = (float)1e-15;                            /* :53 */
-    for (i64 point = 0; point < n_points; point++) {
+    for (i64 li = 0; li < n_list; li++) {
+        const i64 point = list ? list[li] : li;
+        double *weights = weights_out + (li - point) * ncol;               /* weights[point * ncol + k] is row li */
         int zero_found = 0;
         double total = 0.0;
         i64 n_source = 0;
@@ -390,13 +396,22 @@ void orc_idw(i64 dim, i64 n_points, i64 ncol, const i64 *esup_ptr, const i64 *es
     }
 }
 
+void orc_idw(i64 dim, i64 n_points, i64 ncol, const i64 *esup_ptr, const i64 *esup, const i64 *boundary_points,
+             const i64 *neumann_point, const double *coords, const double *centroids, double *weights)
+{
+    orc_idw_nodes(dim, n_points, NULL, ncol, esup_ptr, esup, boundary_points, neumann_point, coords, centroids, weights);
+}
+
 /* ------------------------------------------------------------------------------------------------
  * LSInterpolation.LS — ls.pyx:33-135, all nodes as targets.
  * ---------------------------------------------------------------------------------------------- */
-void orc_ls(i64 n_points, i64 ncol, const i64 *esup_ptr, const i64 *esup, const i64 *boundary_points,
-            const i64 *neumann_point, const double *coords, const double *centroids, double *weights)
+void orc_ls_nodes(i64 n_list, const i64 *list, i64 ncol, const i64 *esup_ptr, const i64 *esup,
+                  const i64 *boundary_points, const i64 *neumann_point, const double *coords, const double *centroids,
+                  double *weights_out)
 {
-    for (i64 point = 0; point < n_points; point++) {
+    for (i64 li = 0; li < n_list; li++) {
+        const i64 point = list ? list[li] : li;
+        double *weights = weights_out + (li - point) * ncol;               /* see orc_idw_nodes */
         double Ix, Iy, Iz, Ixx, Ixy, Ixz, Iyy, Iyz, Izz, D, lx, ly, lz, denom, vx, vy, vz, total;
         if (boundary_points[point] && !neumann_point[point]) continue;
         Ix = Iy = Iz = 0.0;
@@ -444,6 +459,12 @@ void orc_ls(i64 n_points, i64 ncol, const i64 *esup_ptr, const i64 *esup, const 
     }
 }
 
+void orc_ls(i64 n_points, i64 ncol, const i64 *esup_ptr, const i64 *esup, const i64 *boundary_points,
+            const i64 *neumann_point, const double *coords, const double *centroids, double *weights)
+{
+    orc_ls_nodes(n_points, NULL, ncol, esup_ptr, esup, boundary_points, neumann_point, coords, centroids, weights);
+}
+
 /* ------------------------------------------------------------------------------------------------
  * GLSInterpolation.GLS + build_ks_sv_arrays + build_ls_matrices + set_neumann_rows + solve_ls —
  * gls.pyx:75-474, all nodes as targets, one scratch slab (the reference has one per OpenMP thread).
@@ -464,12 +485,12 @@ static void cross3(const double *a, const double *b, double *c)          /* gls.
     c[2] = a[0] * b[1] - a[1] * b[0];
 }
 
-int orc_gls(i64 n_points, i64 MXE, i64 MXF, const i64 *esup_ptr, const i64 *esup, const i64 *fsup_ptr,
+int orc_gls_nodes(i64 n_list, const i64 *list, i64 MXE, i64 MXF, const i64 *esup_ptr, const i64 *esup, const i64 *fsup_ptr,
             const i64 *fsup, const i64 *esuf_ptr, const i64 *esuf, const i64 *inpofa, const i64 *boundary_faces,
             const i64 *boundary_points, const i64 *neumann_point, const double *neumann_val,
             const double *coords, const double *centroids, const double *faces_centers,
             const double *normal_faces, const double *permeability /*[n_elems,3,3]*/, const double *diff_mag,
-            dgels_t dgels, dgemv_t dgemv, double *weights /*[n_points,MXE]*/, double *neumann_ws,
+            dgels_t dgels, dgemv_t dgemv, double *weights_out /*[n_list,MXE]*/, double *neumann_out,
             i64 dump_point, double *dump_M, i64 *dump_mn)
 {
     int M_MAX = (int)(MXE + 3 * MXF + MXF), N_MAX = (int)(3 * MXE + 1), NRHS_MAX = (int)(MXE + 1);
@@ -498,7 +519,10 @@ int orc_gls(i64 n_points, i64 MXE, i64 MXF, const i64 *esup_ptr, const i64 *esup
         B = (double *)malloc(sizeof(double) * (size_t)M_MAX * NRHS_MAX);
         if (!work || !A || !B) return -1;
     }
-    for (i64 point = 0; point < n_points; point++) {
+    for (i64 li = 0; li < n_list; li++) {
+        const i64 point = list ? list[li] : li;                               /* row li of the outputs, see orc_idw_nodes */
+        double *weights = weights_out + (li - point) * MXE;
+        double *neumann_ws = neumann_out + (li - point);
         if (boundary_points[point] && !neumann_point[point]) continue;        /* :165 */
         int n_elem = (int)(esup_ptr[point + 1] - esup_ptr[point]);
         int n_face = (int)(fsup_ptr[point + 1] - fsup_ptr[point]);
@@ -643,6 +667,19 @@ int orc_gls(i64 n_points, i64 MXE, i64 MXF, const i64 *esup_ptr, const i64 *esup
     free(Mi); free(Ni); free(KSetv); free(Sv); free(Svb); free(dKv); free(T1); free(tT2);
     free(nL1); free(nL2); free(nL); free(KsSv); free(KsSvb); free(A); free(B); free(work);
     return 0;
+}
+
+int orc_gls(i64 n_points, i64 MXE, i64 MXF, const i64 *esup_ptr, const i64 *esup, const i64 *fsup_ptr,
+            const i64 *fsup, const i64 *esuf_ptr, const i64 *esuf, const i64 *inpofa, const i64 *boundary_faces,
+            const i64 *boundary_points, const i64 *neumann_point, const double *neumann_val,
+            const double *coords, const double *centroids, const double *faces_centers,
+            const double *normal_faces, const double *permeability, const double *diff_mag,
+            dgels_t dgels, dgemv_t dgemv, double *weights /*[n_points,MXE]*/, double *neumann_ws,
+            i64 dump_point, double *dump_M, i64 *dump_mn)
+{
+    return orc_gls_nodes(n_points, NULL, MXE, MXF, esup_ptr, esup, fsup_ptr, fsup, esuf_ptr, esuf, inpofa, boundary_faces,
+                         boundary_points, neumann_point, neumann_val, coords, centroids, faces_centers, normal_faces,
+                         permeability, diff_mag, dgels, dgemv, weights, neumann_ws, dump_point, dump_M, dump_mn);
 }
 
 /* ------------------------------------------------------------------------------------------------

@@ -1,0 +1,117 @@
+"""Vectorised numpy restatements of the reference's connectivity definitions, used by the at-size parity tests
+(tests/test_gpu_at_size.py) on the arrays exported by the CUDA path, and by tests/test_host.py on the oracle's
+grid (so that the checker itself is tested on the CPU).  Test infrastructure."""
+import numpy as np
+
+
+def check_node_csr(name, ptr, flat, table, n_rows, chunk=1 << 25):
+    """(ptr, flat) is the node -> owner CSR of `table` ([n_owner, width], -1 padded) with ascending rows —
+    the definition of build_esup / build_fsup (grid.pyx:244-267, 354-379): right counts, strictly ascending rows
+    and every entry a true incidence  =>  every row is exactly the sorted set of owners."""
+    valid = table >= 0
+    cnt = np.bincount(table[valid].ravel(), minlength=n_rows)
+    assert ptr[0] == 0 and np.array_equal(np.diff(ptr), cnt), name + ": row lengths"
+    assert len(flat) == ptr[-1]
+    d = np.diff(flat) > 0
+    starts = ptr[1:-1]
+    starts = starts[(starts > 0) & (starts < len(flat))]
+    d[starts - 1] = True                       # a row boundary may go down
+    assert d.all(), name + ": rows not strictly ascending"
+    rows = np.repeat(np.arange(n_rows), cnt)
+    for b in range(0, len(flat), chunk):
+        e = min(len(flat), b + chunk)
+        assert (table[flat[b:e]] == rows[b:e, None]).any(axis=1).all(), name + ": entry is not an incidence"
+
+
+def face_nodes(g, e, j):
+    """node ids of local face j of elements e (vectorised), -1 padded to 4 — grid.pyx:321-345"""
+    t = np.asarray(g.element_types)[e]
+    lp = np.asarray(g.lpofa)[t, j]                       # [m, 4]
+    ln = np.asarray(g.lnofa)[t, j]
+    nodes = np.take_along_axis(np.asarray(g.inpoel)[e], np.where(lp >= 0, lp, 0), axis=1)
+    nodes[np.arange(4)[None, :] >= ln[:, None]] = -1
+    return nodes
+
+
+
+def check_connectivity_and_geometry(g, mesh, rng, oracle):
+    """Every statement below is an assertion about the arrays of `g` (reference layouts); see the module
+    docstring of tests/test_gpu_at_size.py for what is complete and what is sampled."""
+    ne, npts, nf = g.n_elems, g.n_points, g.n_faces
+    inpoel, etype = np.asarray(g.inpoel), np.asarray(g.element_types)
+    # the exported element table is the input, padded like process_mesh pads it (interpolator.pyx:347-361)
+    at = 0
+    for blk in mesh.cells:
+        m, w = blk.data.shape
+        assert np.array_equal(inpoel[at:at + m, :w], blk.data) and (inpoel[at:at + m, w:] == -1).all()
+        at += m
+    assert at == ne
+    # ---- esup / fsup: complete ----
+    esup_ptr, esup = np.asarray(g.esup_ptr), np.asarray(g.esup)
+    check_node_csr("esup", esup_ptr, esup, inpoel, npts)
+    assert g.MX_ELEMENTS_PER_POINT == int(np.diff(esup_ptr).max())
+    inpofa = np.asarray(g.inpofa)
+    fsup_ptr, fsup = np.asarray(g.fsup_ptr), np.asarray(g.fsup)
+    check_node_csr("fsup", fsup_ptr, fsup, inpofa, npts)
+    assert g.MX_FACES_PER_POINT == int(np.diff(fsup_ptr).max())
+    # ---- face numbering: first encounter in (element, local face) order; owner = lower element id ----
+    esuel, infael = np.asarray(g.esuel), np.asarray(g.infael)
+    nfael = np.asarray(g.nfael)[etype]
+    real = np.arange(esuel.shape[1])[None, :] < nfael[:, None]
+    assert (esuel[~real] == -1).all() and (infael[~real] == -1).all()
+    owner = real & ((esuel < 0) | (np.arange(ne)[:, None] < esuel))
+    assert int(owner.sum()) == nf
+    assert np.array_equal(infael[owner], np.arange(nf)), "face ids are not in first-encounter order"
+    esuf_ptr, esuf = np.asarray(g.esuf_ptr), np.asarray(g.esuf)
+    bfaces, bpoints = np.asarray(g.boundary_faces), np.asarray(g.boundary_points)
+    own_e = np.nonzero(owner)[0]
+    assert np.array_equal(esuf[esuf_ptr[:-1]], own_e), "esuf rows must start with the owner"
+    other = esuel[owner]
+    assert np.array_equal(np.diff(esuf_ptr), np.where(other >= 0, 2, 1))
+    assert np.array_equal(esuf[esuf_ptr[:-1][other >= 0] + 1], other[other >= 0])
+    assert np.array_equal(bfaces != 0, other < 0)
+    # non-owners carry the id their neighbour gave the shared face
+    ee, jj = np.nonzero(real & ~owner)
+    pick = rng.choice(len(ee), size=min(len(ee), 4_000_000), replace=False)
+    ee, jj = ee[pick], jj[pick]
+    kk = esuel[ee, jj]
+    back = esuel[kk] == ee[:, None]
+    assert back.any(axis=1).all(), "esuel is not symmetric"
+    ll = back.argmax(axis=1)
+    assert np.array_equal(infael[ee, jj], infael[kk, ll])
+    # the two sides of a sampled interior face have the same node set (grid.pyx:502-512)
+    a, b = np.sort(face_nodes(g, ee, jj), axis=1), np.sort(face_nodes(g, kk, ll), axis=1)
+    assert np.array_equal(a, b), "esuel pairs faces with different nodes"
+    # inpofa = the owner's local ordering (grid.pyx:340-345), sampled
+    fo = rng.choice(nf, size=min(nf, 2_000_000), replace=False)
+    oe, oj = np.nonzero(owner)
+    assert np.array_equal(inpofa[fo], face_nodes(g, oe[fo], oj[fo]))
+    # ---- boundary tags against an independent geometric criterion: a face of these box meshes is a boundary
+    #      face iff all its nodes lie on one side of the hull ----
+    P = np.asarray(g.point_coords)
+    assert np.array_equal(P, np.asarray(mesh.points, dtype=np.float64))
+    side = np.stack([P[:, 0] == 0.0, P[:, 0] == 1.0, P[:, 1] == 0.0, P[:, 1] == 1.0, P[:, 2] == 0.0, P[:, 2] == 1.0], axis=1)
+    on = np.ones((nf, 6), dtype=bool)
+    for c in range(4):
+        col = inpofa[:, c]
+        on &= np.where((col >= 0)[:, None], side[np.where(col >= 0, col, 0)], True)
+    assert np.array_equal(on.any(axis=1), bfaces != 0), "boundary_faces disagree with the hull geometry"
+    assert np.array_equal(side.any(axis=1), bpoints != 0), "boundary_points disagree with the hull geometry"
+    del on
+    # ---- geometry on samples, through the C oracle (grid.pyx:669-809) ----
+    L = oracle.lib()
+    P_, LL = oracle._p, oracle._ll
+    se = np.sort(rng.choice(ne, size=min(ne, 500_000), replace=False))
+    sf = np.sort(rng.choice(nf, size=min(nf, 500_000), replace=False))
+    sub_inpoel, sub_et, sub_inpofa = np.ascontiguousarray(inpoel[se]), np.ascontiguousarray(etype[se]), np.ascontiguousarray(inpofa[sf])
+    cen = np.zeros((len(se), 3))
+    fcen = np.zeros((len(sf), 3))
+    npoel_t = np.ascontiguousarray(g.npoel, dtype=np.int64)
+    L.orc_centroids(LL(3), LL(len(se)), LL(len(sf)), P_(sub_inpoel), P_(sub_et), P_(npoel_t), P_(sub_inpofa), P_(P), P_(cen), P_(fcen))
+    nrm = np.zeros((len(sf), 3))
+    area = np.zeros(len(sf))
+    L.orc_normals(LL(3), LL(len(sf)), P_(sub_inpofa), P_(P), P_(nrm), P_(area))
+    centroids, fcenters = np.asarray(g.centroids), np.asarray(g.faces_centers)
+    normals, areas = np.asarray(g.normal_faces), np.asarray(g.faces_areas)
+    assert np.array_equal(centroids[se], cen) and np.array_equal(fcenters[sf], fcen)
+    assert np.array_equal(normals[sf], nrm) and np.array_equal(areas[sf], area)
