@@ -146,13 +146,24 @@ int npb_interpolate_fetch(npb_ctx *ctx, int32_t *indptr, int32_t *indices, doubl
 int npb_interpolate_dense(npb_ctx *ctx, int method, double *weights, double *neumann_ws);
 
 /* The same result as npb_interpolate_count + npb_interpolate_fetch, computed as a pipeline over n_chunks
- * contiguous node chunks on one GPU: the cell-field slice of chunk k+1 is uploaded and the CSR block of
- * chunk k-1 is downloaded while chunk k computes (three CUDA streams).  perm_host / diff_mag_host: the
- * full host arrays (9*n_elems / n_elems doubles) to upload slice by slice for GLS, or NULL to use the
- * fields already set with npb_set_cell_field.  indices / data must hold `capacity` entries, with
- * capacity >= the number of node->element incidences (grid scalar "len_esup"), the upper bound of nnz;
- * indptr n_points+1, neumann n_points.  All host arrays must be page-locked.  No reference counterpart
- * (host orchestration of interpolator.pyx:579-624 for a device that sits behind PCIe). */
+ * contiguous node chunks of THIS RANK's node range (one GPU: all nodes).  The CSR row lengths are planned before
+ * the weights exist (a Dirichlet node emits nothing, every other node its whole node->element row), so every rank
+ * knows the global indptr without any exchange and four streams overlap: upload of the cell-field slice chunk k+1
+ * reads (GLS; perm_host / diff_mag_host = the full page-locked host arrays, or NULL to use the fields already set),
+ * compute of chunk k at its final global offsets, (gather = NPB_GATHER_ALL) NCCL broadcast of chunk k to the peers,
+ * download of the finished blocks into the caller's page-locked arrays (NPB_GATHER_HOST: this rank's rows at their
+ * global positions of arrays shared by the ranks; otherwise the whole CSR).  Any of indptr / indices / data /
+ * neumann may be NULL (device-resident result only: what bench.py's device-timed `value` measures); indices / data
+ * hold `capacity` entries, capacity >= the planned nnz (<= grid scalar "len_esup").
+ * *fell_back = 1 (identically on every rank) when some rank met an exact-zero weight - scipy's eliminate_zeros
+ * would drop it, which voids the planned offsets - or a node star too large for the tile kernels: nothing valid was
+ * written and the caller runs npb_interpolate_count + npb_interpolate_fetch instead.  Not for NPB_GATHER_ROOT.
+ * No reference counterpart (host orchestration of interpolator.pyx:579-624 for a device behind PCIe / NVLink). */
+int npb_interpolate_run(npb_ctx *ctx, int method, int n_chunks, const double *perm_host, const double *diff_mag_host,
+                        int32_t *indptr, int32_t *indices, double *data, double *neumann, int64_t capacity,
+                        int64_t *nnz, int *fell_back);
+/* Round-1 entry point of the single-GPU pipeline: npb_interpolate_run with all four outputs required and the
+ * two-pass fallback taken internally. */
 int npb_interpolate_streamed(npb_ctx *ctx, int method, int n_chunks, const double *perm_host,
                              const double *diff_mag_host, int32_t *indptr, int32_t *indices, double *data,
                              double *neumann, int64_t capacity, int64_t *nnz);

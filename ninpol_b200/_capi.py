@@ -39,6 +39,8 @@ _SIGNATURES = {
     "npb_interpolate_count": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_i64p]),
     "npb_interpolate_fetch": (ctypes.c_int, [ctypes.c_void_p] * 5),
     "npb_interpolate_dense": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "npb_interpolate_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 6
+                            + [ctypes.c_int64, _c_i64p, ctypes.POINTER(ctypes.c_int)]),
     "npb_interpolate_streamed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 6 + [ctypes.c_int64, _c_i64p]),
     "npb_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]),
     "npb_launch_count": (ctypes.c_int, [ctypes.c_void_p, _c_i64p]),
@@ -189,8 +191,19 @@ class Context:
         check(self.lib.npb_set_point_flags(self.handle, _ptr(f), f.size))
 
     # --- K2 / K3 / K4 ---
+    def interpolate_run(self, method, n_chunks, perm=None, diff_mag=None, indptr=None, indices=None, data=None, neumann=None):
+        """Chunk pipeline over this rank's nodes (pipeline.cu).  Host arrays page-locked or None.  Returns
+        (nnz, fell_back); fell_back = True (on every rank alike): nothing valid was written, run count + fetch."""
+        nnz = ctypes.c_int64(0)
+        fb = ctypes.c_int(0)
+        cap = min(indices.size, data.size) if (indices is not None and data is not None) else 0
+        check(self.lib.npb_interpolate_run(self.handle, METHOD_IDS[method], int(n_chunks), _ptr(perm), _ptr(diff_mag),
+                                           _ptr(indptr), _ptr(indices), _ptr(data), _ptr(neumann), int(cap),
+                                           ctypes.byref(nnz), ctypes.byref(fb)))
+        return int(nnz.value), bool(fb.value)
+
     def interpolate_streamed(self, method, n_chunks, perm, diff_mag, indptr, indices, data, neumann):
-        """Pipelined count + fetch (stream.cu); all arrays page-locked, indices / data sized for len_esup."""
+        """Single-GPU pipeline with the internal two-pass fallback (pipeline.cu); all arrays page-locked."""
         nnz = ctypes.c_int64(0)
         check(self.lib.npb_interpolate_streamed(self.handle, METHOD_IDS[method], int(n_chunks),
                                                 _ptr(perm) if perm is not None else None,

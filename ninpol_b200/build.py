@@ -31,7 +31,7 @@ UNITS = {
     "k2_gls_dense.cu": [],
     "k3_emit.cu": [],
     "k4_shard.cu": [],
-    "stream.cu": [],
+    "pipeline.cu": [],
 }
 
 

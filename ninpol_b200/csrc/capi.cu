@@ -50,6 +50,11 @@ int npb_ensure(void **p, size_t *cap, size_t bytes)
 }
 
 __global__ void k_copy_int(int *dst, const int *src) { *dst = *src; }
+__global__ void k_copy2_int(int *dst, const int *src)
+{
+    dst[0] = src[0];
+    dst[1] = src[1];
+}
 
 int npb_read_int(npb_ctx *c, const int *d_src, int *h_out)
 {
@@ -200,6 +205,8 @@ static void free_mesh(npb_ctx *c)
     c->fused_failed[0] = c->fused_failed[1] = false;
     c->mesh_loaded = false;
     c->counted = false;
+    c->plan_kind = 0;
+    c->plan_chunks = 0;
 }
 
 extern "C" int npb_create(int device, npb_ctx **out)
@@ -271,6 +278,7 @@ extern "C" int npb_destroy(npb_ctx *c)
     for (cudaEvent_t e : c->pipe_ev) cudaEventDestroy(e);
     if (c->up_stream) cudaStreamDestroy(c->up_stream);
     if (c->down_stream) cudaStreamDestroy(c->down_stream);
+    if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_b) cudaEventDestroy(c->ev_b);
     cudaStreamDestroy(c->stream);
@@ -304,6 +312,7 @@ static int refresh_range(npb_ctx *c)
     c->wbase = b[0];
     c->wlen = (i64)b[1] - b[0];
     c->counted = false;
+    c->plan_chunks = 0;   // chunk boundaries follow the rank bounds
     return NPB_OK;
 }
 
@@ -498,6 +507,7 @@ extern "C" int npb_grid_scalar(npb_ctx *c, const char *name, int64_t *out)
         {"MX_ELEMENTS_PER_FACE", c->mx_epf}, {"MX_FACES_PER_POINT", c->mx_fpp}, {"len_esup", c->len_esup},
         {"len_fsup", c->len_fsup}, {"len_esuf", c->len_esuf}, {"len_psup", c->len_psup},
         {"row_lo", c->lo}, {"row_hi", c->hi}, {"rank", c->rank}, {"world", c->world}, {"sm_count", c->sm_count},
+        {"have_cell_fields", (c->have_perm && c->have_dm) ? 1 : 0}, {"plan_nnz", c->plan_nnz},
     };
     for (auto &e : tbl)
         if (strcmp(e.n, name) == 0) {
@@ -614,6 +624,7 @@ extern "C" int npb_set_point_flags(npb_ctx *c, const int64_t *flag, int64_t n_po
     NPB_CUDA(cudaStreamSynchronize(c->stream));
     c->have_flags = true;
     c->counted = false;
+    c->plan_kind = 0;     // row lengths depend on the flags
     c->fused_failed[0] = c->fused_failed[1] = false;
     return NPB_OK;
 }
@@ -647,6 +658,7 @@ extern "C" int npb_set_point_flags_f64(npb_ctx *c, const double *flag, int64_t n
     NPB_CUDA(cudaStreamSynchronize(c->stream));
     c->have_flags = true;
     c->counted = false;
+    c->plan_kind = 0;     // row lengths depend on the flags
     c->fused_failed[0] = c->fused_failed[1] = false;
     return NPB_OK;
 }
@@ -676,6 +688,8 @@ extern "C" int npb_interpolate_count(npb_ctx *c, int method, int64_t *nnz)
     NPB_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     c->filled = false;
+    c->gathered = false;
+    c->plan_kind = 0;     // this path rewrites indptr / neumann
     if (method != NPB_METHOD_GLS && !c->fused_failed[method]) {
         // fused K2+K3 (k2_idw_ls_tile.cu): final CSR in one pass unless a weight is an exact zero
         NpbTimer tm(c, "k2");
@@ -783,7 +797,7 @@ extern "C" int npb_interpolate_fetch(npb_ctx *c, int32_t *indptr, int32_t *indic
         c->filled = true;
     }
     const bool host_gather = c->world > 1 && c->gather_mode == NPB_GATHER_HOST;
-    if (c->world > 1 && !host_gather) {
+    if (c->world > 1 && !host_gather && !c->gathered) {
         NpbTimer tm(c, "k4_gather");
         NPB_TRY(npb_k4_gather_blocks(c));
         tm.stop();

@@ -122,8 +122,14 @@ struct npb_ctx {
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;  // npb_timer_start / stop
     void *stage[2] = {nullptr, nullptr};         // page-locked staging buffers for pageable host memory
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
-    cudaStream_t up_stream = nullptr, down_stream = nullptr;   // stream.cu: upload / download legs of the pipeline
+    cudaStream_t up_stream = nullptr, down_stream = nullptr, comm_stream = nullptr;   // pipeline.cu: upload / download / gather legs
     std::vector<cudaEvent_t> pipe_ev;
+    // pipeline.cu: the optimistic row plan (c->indptr holds it while plan_kind != 0: 1 = IDW / LS, 2 = GLS)
+    int plan_kind = 0;
+    i64 plan_nnz = 0;
+    int plan_chunks = 0;                 // chunk table below is valid for this many chunks per rank
+    std::vector<i64> chunk_node, chunk_nz;   // [world * K + 1] node / nnz boundaries of every rank's chunks
+    bool gathered = false;               // indices / data / neumann of ALL ranks are on this device (gather = all)
 };
 
 // ---- helpers implemented in capi.cu ----
@@ -161,7 +167,8 @@ int npb_k2_idw_ls_tiles(npb_ctx *c, int method, i64 lo, i64 hi, int *used);
 int npb_ensure_out(npb_ctx *c, size_t n);
 int npb_k2_gls(npb_ctx *c, i64 lo, i64 hi);
 int npb_k3_fill(npb_ctx *c, i64 lo, i64 hi);
-int npb_read_int(npb_ctx *c, const int *d_src, int *h_out);   // device int -> host through the mapped block + stream sync
+int npb_read_int(npb_ctx *c, const int *d_src, int *h_out);
+__global__ void k_copy2_int(int *dst, const int *src);   // capi.cu: two ints, device -> mapped host block   // device int -> host through the mapped block + stream sync
 int npb_minmax_i32(npb_ctx *c, const int32_t *in, i64 n, int32_t *h_min, int32_t *h_max);
 int npb_k4_gather_counts(npb_ctx *c);
 int npb_k4_gather_blocks(npb_ctx *c);

@@ -353,6 +353,19 @@ int npb_k2_idw_ls_tiles(npb_ctx *c, int method, i64 lo, i64 hi, int *used)
     return tile_launch(c, a, method);
 }
 
+// Direct mode over a node range with c->indptr already holding the (optimistic) global plan and c->indices /
+// c->data sized for it (pipeline.cu): exact zeros are counted in counters[45], which the caller reads.
+int npb_k2_idw_ls_direct(npb_ctx *c, int method, i64 lo, i64 hi, int *used)
+{
+    *used = 0;
+    if (tile_nb(c, method) < 1) return NPB_OK;
+    *used = 1;
+    if (hi <= lo) return NPB_OK;
+    TileArgs a;
+    tile_args(c, a, method, lo, hi, 1);
+    return tile_launch(c, a, method);
+}
+
 // Single-pass mode: *used = 1 when indptr / indices / data / neumann hold the final CSR, 0 when the
 // caller has to run the two-pass path instead (multi-GPU, oversized stars, or an exact-zero weight).
 int npb_k2_idw_ls_fused(npb_ctx *c, int method, int *used)

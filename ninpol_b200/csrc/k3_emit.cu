@@ -15,7 +15,7 @@ template <int W>
 __global__ void __launch_bounds__(256)
 k_emit_rows(const int32_t *__restrict__ esup_ptr, const int32_t *__restrict__ esup, const double *__restrict__ wbuf,
             i64 wbase, const int32_t *__restrict__ indptr, i64 lo, i64 hi, int32_t *__restrict__ indices,
-            double *__restrict__ data)
+            double *__restrict__ data, const int32_t *__restrict__ rowcnt, int *__restrict__ mismatch)
 {
     const i64 gt = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & (W - 1);
@@ -26,9 +26,16 @@ k_emit_rows(const int32_t *__restrict__ esup_ptr, const int32_t *__restrict__ es
     int out0 = 0, b = 0, e = 0;
     if (live) {
         out0 = indptr[p];
-        if (indptr[p + 1] != out0) {
+        const int planned = indptr[p + 1] - out0;
+        if (planned != 0) {
             b = esup_ptr[p];
             e = esup_ptr[p + 1];
+        }
+        // planned mode (pipeline.cu): indptr was fixed before the weights were known; a row that kept fewer or
+        // more entries than planned voids the plan (and is not written)
+        if (rowcnt && rowcnt[p] != planned) {
+            if (lane == 0) atomicAdd(mismatch, 1);
+            e = b;
         }
     }
     // all groups of a warp iterate together (the ballot is warp wide): up to the longest row of the warp
@@ -55,20 +62,29 @@ k_emit_rows(const int32_t *__restrict__ esup_ptr, const int32_t *__restrict__ es
     }
 }
 
-int npb_k3_fill(npb_ctx *c, i64 lo, i64 hi)
+static int emit(npb_ctx *c, i64 lo, i64 hi, const int32_t *rowcnt, int *mismatch)
 {
     if (hi <= lo) return NPB_OK;
     const int T = 256;
     if (c->mx_epp <= 16) {
         i64 threads = (hi - lo) * 8;
         k_emit_rows<8><<<npb_blocks(threads, T), T, 0, c->stream>>>(c->esup_ptr, c->esup, c->wbuf, c->wbase, c->indptr, lo, hi,
-                                                                   c->indices, c->data);
+                                                                   c->indices, c->data, rowcnt, mismatch);
     } else {
         i64 threads = (hi - lo) * 32;
         k_emit_rows<32><<<npb_blocks(threads, T), T, 0, c->stream>>>(c->esup_ptr, c->esup, c->wbuf, c->wbase, c->indptr, lo, hi,
-                                                                    c->indices, c->data);
+                                                                    c->indices, c->data, rowcnt, mismatch);
     }
     NPB_LAUNCH(c);
     NPB_CUDA(cudaGetLastError());
     return NPB_OK;
+}
+
+int npb_k3_fill(npb_ctx *c, i64 lo, i64 hi) { return emit(c, lo, hi, nullptr, nullptr); }
+
+// rows [lo, hi) at the offsets of the optimistic plan; *mismatch_counter counts rows whose surviving entries
+// differ from the planned length (an exact-zero weight): the caller then discards the result
+int npb_k3_fill_planned(npb_ctx *c, i64 lo, i64 hi, int *mismatch_counter)
+{
+    return emit(c, lo, hi, c->rowcnt, mismatch_counter);
 }

@@ -185,3 +185,58 @@ int npb_k4_gather_blocks(npb_ctx *c)
     NPB_NCCL(api->GroupEnd());
     return NPB_OK;
 }
+
+// Every rank contributes one int; *any = 1 when some rank's is non-zero.  One grouped 1-int broadcast per rank on
+// the compute stream (the same exchange as npb_comm_barrier), then the world ints come back through the mapped block.
+__global__ void k_set_int(int *p, int v) { *p = v; }
+__global__ void k_copy_ints(int *dst, const int *src, int n)
+{
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
+int npb_k4_share_flags(npb_ctx *c, int mine, int *any)
+{
+    *any = mine;
+    if (c->world == 1) return NPB_OK;
+    if (c->world > 16) {
+        npb_set_error("npb_k4_share_flags: world > 16 not supported");
+        return NPB_ERR_ARG;
+    }
+    NcclApi *api = c->nccl;
+    ncclComm_t comm = (ncclComm_t)c->comm;
+    int *buf = c->counters + 48;
+    k_set_int<<<1, 1, 0, c->stream>>>(buf + c->rank, mine);
+    NPB_LAUNCH(c);
+    NPB_NCCL(api->GroupStart());
+    for (int r = 0; r < c->world; r++) NPB_NCCL(api->Broadcast(buf + r, buf + r, 1, ncclInt32, r, comm, c->stream));
+    NPB_NCCL(api->GroupEnd());
+    k_copy_ints<<<1, 32, 0, c->stream>>>(c->d_small + 16, buf, c->world);
+    NPB_LAUNCH(c);
+    NPB_CUDA(cudaStreamSynchronize(c->stream));
+    int a = 0;
+    for (int r = 0; r < c->world; r++) a |= (c->h_small[16 + r] != 0);
+    *any = a;
+    return NPB_OK;
+}
+
+// One chunk step of the pipelined all-gather-v: rank r owns nodes [node_lo[r], node_hi[r]) = CSR entries
+// [nz_lo[r], nz_hi[r]); every rank receives every block at its final position (in-place grouped broadcasts on `st`).
+int npb_k4_bcast_chunk(npb_ctx *c, cudaStream_t st, const std::vector<i64> &node_lo, const std::vector<i64> &node_hi,
+                       const std::vector<i64> &nz_lo, const std::vector<i64> &nz_hi, bool with_neumann)
+{
+    if (c->world == 1) return NPB_OK;
+    NcclApi *api = c->nccl;
+    ncclComm_t comm = (ncclComm_t)c->comm;
+    NPB_NCCL(api->GroupStart());
+    for (int r = 0; r < c->world; r++) {
+        const i64 rows = node_hi[r] - node_lo[r], nk = nz_hi[r] - nz_lo[r];
+        if (with_neumann && rows > 0)
+            NPB_NCCL(api->Broadcast(c->neumann + node_lo[r], c->neumann + node_lo[r], (size_t)rows, ncclFloat64, r, comm, st));
+        if (nk > 0) {
+            NPB_NCCL(api->Broadcast(c->indices + nz_lo[r], c->indices + nz_lo[r], (size_t)nk, ncclInt32, r, comm, st));
+            NPB_NCCL(api->Broadcast(c->data + nz_lo[r], c->data + nz_lo[r], (size_t)nk, ncclFloat64, r, comm, st));
+        }
+    }
+    NPB_NCCL(api->GroupEnd());
+    return NPB_OK;
+}

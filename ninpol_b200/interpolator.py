@@ -15,6 +15,7 @@ geometry, the per-node weights and the CSR emit all run on the GPU.  There is no
 import os
 import struct
 import pickle
+import sys
 import tempfile
 import time
 
@@ -76,17 +77,50 @@ class _Method:
     __call__ = prepare
 
 
+class _PinnedPool:
+    """Page-locked output buffers that are reused ONLY when nothing else refers to them any more.
+
+    interpolate() hands out numpy views of cudaHostAlloc blocks (full-rate, overlappable device->host copies).  A
+    block goes back into circulation when the arrays made from it - and the scipy matrix holding them - are gone,
+    which the owner's reference count tells; as long as the caller keeps a result it is never overwritten, so the
+    drop-in semantics of the reference (fresh arrays per call) hold while a loop that drops its previous result
+    runs without allocating."""
+
+    def __init__(self):
+        self._blocks = {}   # name -> list of _PinnedOwner-backed base arrays
+
+    def take(self, name, n, dtype):
+        dtype = np.dtype(dtype)
+        free = None
+        for owner in self._blocks.setdefault(name, []):
+            # references: the list, the loop variable and getrefcount's argument; a live view adds one
+            if owner.dtype == dtype and owner.size >= n and sys.getrefcount(owner) <= 3:
+                if free is None or owner.size < free.size:
+                    free = owner
+        if free is None:
+            free = _capi.pinned_empty(n + n // 16 + 16, dtype)
+            # keep at most two idle generations per name: drop smaller unused blocks
+            self._blocks[name] = [o for o in self._blocks[name] if sys.getrefcount(o) > 3 or o.size >= n][-3:]
+            self._blocks[name].append(free)
+        return free[:n]
+
+    def clear(self):
+        self._blocks = {}
+
+
 class Interpolator:
     def __init__(self, name="interpolator", logging=False, build_edges=False, device=None, comm=None,
-                 pinned_outputs=False, pin_inputs=False, gather="all", stream_chunks=0):
-        # pinned_outputs=True: the CSR / neumann arrays returned by interpolate() live in page-locked
-        # buffers that are REUSED by the next interpolate() call (faster device->host copies)
+                 pinned_outputs=True, pin_inputs=True, gather="all", stream_chunks=8):
+        # pinned_outputs=True (default): the CSR / neumann arrays returned by interpolate() are views of page-locked
+        # blocks from a pool; a block is reused only once the caller has dropped every array made from it
+        # (_PinnedPool), so results are never overwritten behind the caller's back.  False: plain numpy arrays.
         self.pinned_outputs = pinned_outputs
-        self._pinned = {}
-        # pin_inputs=True: the per-variable host arrays (permeability, diff_mag, flags) are page-locked in
-        # place the first time they are uploaded, so repeated uploads run at the PCIe rate
+        self._pool = _PinnedPool()
+        # pin_inputs=True (default): the per-variable host arrays (permeability, diff_mag, flags) are page-locked in
+        # place (cudaHostRegister) the first time they are uploaded, so uploads run at the PCIe rate and overlap
         self.pin_inputs = pin_inputs
         self._registered = {}
+        self._data_version = 0
         self.point_ordering = et.POINT_ORDERING
         self.is_grid_initialized = False
         self.build_edges = build_edges
@@ -124,14 +158,15 @@ class Interpolator:
         if gather not in ("all", "root", "host"):
             raise ValueError("gather must be 'all', 'root' or 'host'")
         self.gather = gather
-        # stream_chunks=K > 0 (single GPU, needs pinned_outputs and pin_inputs): interpolate() runs as a
-        # pipeline over K node chunks - uploads of the GLS cell fields and downloads of the CSR blocks
-        # overlap the kernels (npb_interpolate_streamed); results are bit-identical to the plain path
+        # stream_chunks=K > 0 (default 8): interpolate() runs as a pipeline over K chunks of this rank's nodes -
+        # uploads of the GLS cell fields, the kernels, the NCCL gather and the downloads of the CSR blocks overlap
+        # (npb_interpolate_run); results are bit-identical to the plain count + fetch path (stream_chunks=0)
         self.stream_chunks = int(stream_chunks)
         if self.comm.world > 1:
             self._ctx.comm_init(self.comm.unique_id, self.comm.rank, self.comm.world)
             self._ctx.set_gather(gather)
         self._staged = None
+        self._pending_key = None
         self._partition_key = None
         self._shared, self._shared_reg, self._mesh_serial = None, None, 0
         self.last_timings = {}
@@ -149,6 +184,8 @@ class Interpolator:
     def _set_dense(self, kind, value):
         self._dense[kind] = value
         self._rows[kind] = list(value)
+        self._data_version += 1      # whatever is resident on the device no longer matches
+        self._staged = None
 
     cells_data = property(lambda self: self._dense_view("cells"), lambda self, v: self._set_dense("cells", v))
     points_data = property(lambda self: self._dense_view("points"), lambda self, v: self._set_dense("points", v))
@@ -231,6 +268,8 @@ class Interpolator:
             reg.release()
         self._registered = {}
         self._staged = None
+        self._pending_key = None
+        self._data_version += 1
         self._partition_key = None
         self._shared, self._shared_reg = None, None      # gather="host": a new mapping per mesh
         self._mesh_serial += 1
@@ -306,6 +345,8 @@ class Interpolator:
         kind = "cells" if data_type == "cells" else "points"
         self._rows[kind] = rows
         self._dense[kind] = None
+        self._data_version += 1
+        self._staged = None
         if data_type == "cells":
             self.cells_data_dimensions = dims
         else:
@@ -384,10 +425,13 @@ class Interpolator:
 
     def _stage_inputs(self, method, variable, variable_to_index, cells_data, points_data, defer_fields=False):
         """Uploads what the plug-in of `method` reads for `variable` (idw.pyx:27-28, ls.pyx:28-29,
-        gls.pyx:47-59).  Missing names raise KeyError like the reference's dict lookups."""
+        gls.pyx:47-59).  Missing names raise KeyError like the reference's dict lookups.
+        defer_fields: the pipeline uploads permeability / diff_mag itself, slice by slice; returns them."""
         g = self.grid
-        key = (method == "gls", variable, id(cells_data), id(points_data))
-        flag_index = None
+        # resident inputs are identified by a data-version counter (bumped by load_mesh / load_data / the
+        # cells_data / points_data setters), not by object identity
+        own = cells_data is self._rows["cells"] and points_data is self._rows["points"]
+        key = (method == "gls", variable, self._data_version) if own else None
         if method == "gls":
             permeability_index = variable_to_index["cells"]["permeability"]
             diff_mag_index = variable_to_index["cells"]["diff_mag"]
@@ -395,8 +439,9 @@ class Interpolator:
             variable_to_index["points"]["neumann_" + variable]   # looked up (KeyError) but dead
         else:
             flag_index = variable_to_index["points"]["neumann_flag_" + variable]
-        if self._staged == key:
+        if key is not None and self._staged == key:
             return None
+        self._staged = None
         flags = np.asarray(points_data[flag_index])[:g.n_points]
         if flags.dtype == DTYPE_F and flags.flags.c_contiguous:
             flags = self._maybe_pin("neumann_flag", flags)     # truncated like .astype(int) on the device
@@ -404,16 +449,19 @@ class Interpolator:
             flags = flags.astype(DTYPE_I)
         self._ctx.set_point_flags(flags)
         self._flags_host = flags
-        self._staged = key
         h2d = flags.nbytes
+        self._partition_key = None
         self._set_partition(method)        # the node ranges depend on the flags (skipped nodes cost nothing)
+        fields = None
         if method == "gls":
             perm = np.ascontiguousarray(np.asarray(cells_data[permeability_index])[:g.n_elems * 9], dtype=DTYPE_F)
             dm = np.ascontiguousarray(np.asarray(cells_data[diff_mag_index])[:g.n_elems], dtype=DTYPE_F)
             perm, dm = self._maybe_pin("permeability", perm, defer_fields), self._maybe_pin("diff_mag", dm, defer_fields)
-            if defer_fields and "permeability" in self._registered and "diff_mag" in self._registered:
-                # the streamed pipeline uploads them slice by slice, overlapped with the kernels
-                self.last_timings["h2d_input_bytes"] = h2d + perm.nbytes + dm.nbytes
+            if defer_fields and self._is_registered("permeability", perm) and self._is_registered("diff_mag", dm):
+                # the pipeline uploads them slice by slice, overlapped with the kernels; the key is set by the
+                # caller once that call has succeeded
+                self._pending_key = key
+                self.last_timings["h2d_input_bytes"] = h2d    # + the slices, added by the pipeline
                 return perm, dm
             if self.comm.world > 1:
                 # a rank's nodes read the cell fields of the elements in their own esup rows only
@@ -427,7 +475,13 @@ class Interpolator:
                 self._ctx.set_cell_field("diff_mag", dm)
                 h2d += perm.nbytes + dm.nbytes
         self.last_timings["h2d_input_bytes"] = h2d
-        return None
+        self._staged = key                 # only now: every upload has succeeded
+        self._pending_key = None
+        return fields
+
+    def _is_registered(self, name, arr):
+        reg = self._registered.get(name)
+        return reg is not None and reg.array is not None and reg.array.ctypes.data == arr.ctypes.data
 
     def _maybe_pin(self, name, arr, force=False):
         if not self.pin_inputs or (arr.nbytes < (8 << 20) and not force) or arr.nbytes == 0:
@@ -474,6 +528,9 @@ class Interpolator:
         self._shared = so
         return so
 
+    def _ctx_has_fields(self):
+        return self._ctx.scalar("have_cell_fields") != 0
+
     def invalidate_inputs(self):
         """Forget which per-variable inputs are resident on the device: the next interpolate() uploads
         the flags (and, for GLS, permeability + diff_mag) again from host memory."""
@@ -482,7 +539,7 @@ class Interpolator:
     def _set_partition(self, method):
         if self.comm.world == 1:
             return
-        key = (method == "gls", self._staged)
+        key = (method == "gls", self._data_version, self._mesh_serial)
         if self._partition_key == key:
             return
         g = self.grid
@@ -496,24 +553,54 @@ class Interpolator:
     def _out(self, name, n, dtype):
         if not self.pinned_outputs:
             return np.empty(n, dtype=dtype)
-        buf = self._pinned.get(name)
-        if buf is None or buf.size < n or buf.dtype != np.dtype(dtype):
-            buf = _capi.pinned_empty(n + n // 16 + 16, dtype)
-            self._pinned[name] = buf
-        return buf[:n]
+        return self._pool.take(name, n, dtype)
 
-    def _run_streamed(self, method, fields):
-        g = self.grid
-        n_points, cap = g.n_points, max(1, self._ctx.scalar("len_esup"))
-        indptr = self._out("indptr", n_points + 1, np.int32)
-        indices = self._out("indices", cap, np.int32)
-        data = self._out("data", cap, np.float64)
-        neumann = self._out("neumann", n_points, np.float64)
+    def _run_pipeline(self, method, fields):
+        """npb_interpolate_run: plan, then chunks of this rank's nodes through upload / compute / gather / download
+        streams.  Returns None when the plan was voided (an exact-zero weight somewhere): the caller falls back to the
+        two-pass path - every rank takes the same decision."""
+        g, ctx = self.grid, self._ctx
+        n_points, cap = g.n_points, max(1, ctx.scalar("len_esup"))
         perm, dm = fields if fields is not None else (None, None)
-        nnz = self._ctx.interpolate_streamed(method, self.stream_chunks, perm, dm, indptr, indices, data, neumann)
-        self.last_timings.update({"streamed_ms": self._ctx.timing_or("streamed"), "nnz": nnz,
-                                  "d2h_bytes": indptr.nbytes + neumann.nbytes + 12 * nnz})
-        return indptr, indices[:nnz], data[:nnz], neumann
+        world = self.comm.world
+        if world > 1 and self.gather == "host":
+            so = self._shared_outputs()
+            ctx.comm_barrier()        # every rank is done with the arrays of the previous call
+            pinned = self._shared_reg is not None
+            arrays = (so.indptr, so.indices, so.data, so.neumann)
+        else:
+            arrays = (self._out("indptr", n_points + 1, np.int32), self._out("indices", cap, np.int32),
+                      self._out("data", cap, np.float64), self._out("neumann", n_points, np.float64))
+            pinned = self.pinned_outputs
+        # chunks only pay when a chunk is long next to the launch / copy latencies: ~200k nodes each at least
+        lo_hi = (0, n_points) if world == 1 else (int(self.partition_bounds[self.comm.rank]), int(self.partition_bounds[self.comm.rank + 1]))
+        chunks = max(1, min(self.stream_chunks, (lo_hi[1] - lo_hi[0]) // 200_000))
+        if world > 1:                 # every rank must cut the same number of chunks (the NCCL gather is chunked alike)
+            chunks = max(1, min(self.stream_chunks, n_points // (200_000 * world)))
+        if pinned:
+            nnz, fell_back = ctx.interpolate_run(method, chunks, perm, dm, *arrays)
+        else:                         # pageable outputs: device-resident run, then the staged copies of fetch
+            nnz, fell_back = ctx.interpolate_run(method, chunks, perm, dm)
+            if not fell_back:
+                ctx.interpolate_fetch(*arrays)
+        if fell_back:
+            return None
+        indptr, indices, data, neumann = arrays
+        if world > 1 and self.gather == "host":
+            lo, hi = int(self.partition_bounds[self.comm.rank]), int(self.partition_bounds[self.comm.rank + 1])
+            self.last_timings["d2h_bytes"] = 12 * int(so.indptr[hi] - so.indptr[lo]) + 12 * (hi - lo)   # this rank's rows
+            out = (so.exact("indptr", n_points + 1), so.exact("indices", nnz), so.exact("data", nnz), so.exact("neumann", n_points))
+        else:
+            self.last_timings["d2h_bytes"] = indptr.nbytes + neumann.nbytes + 12 * nnz
+            out = (indptr, indices[:nnz], data[:nnz], neumann)
+        if perm is not None:
+            if world > 1:
+                first, last = ctx.partition_elem_range()
+                self.last_timings["h2d_input_bytes"] += 80 * max(0, last - first + 1)
+            else:
+                self.last_timings["h2d_input_bytes"] += perm.nbytes + dm.nbytes
+        self.last_timings.update({"streamed_ms": ctx.timing_or("streamed"), "nnz": nnz})
+        return out
 
     def _run(self, method):
         g = self.grid
@@ -557,13 +644,19 @@ class Interpolator:
             raise ValueError(f"Variable '{variable}' has more than one dimension. Vector data not supported yet.")
         self._check_targets(target_points)
         self.logger.log(f"Interpolating variable '{variable}' using method '{method}'")
-        streamed = self.stream_chunks > 0 and self.comm.world == 1 and self.pinned_outputs and self.pin_inputs
+        piped = self.stream_chunks > 0 and not (self.comm.world > 1 and self.gather == "root")
         fields = self._stage_inputs(method, variable, self.variable_to_index, self._rows["cells"], self._rows["points"],
-                                    defer_fields=streamed)
-        if streamed:
-            indptr, indices, data, neumann = self._run_streamed(method, fields)
-        else:
-            indptr, indices, data, neumann = self._run(method)
+                                    defer_fields=piped and self.pin_inputs)
+        out = self._run_pipeline(method, fields) if piped else None
+        if out is None:
+            if fields is not None and not (self._ctx_has_fields()):
+                # the pipeline never ran (or gave up before its uploads): stage the cell fields the classic way
+                fields = None
+                self._stage_inputs(method, variable, self.variable_to_index, self._rows["cells"], self._rows["points"])
+            out = self._run(method)
+        if getattr(self, "_pending_key", None) is not None:
+            self._staged, self._pending_key = self._pending_key, None
+        indptr, indices, data, neumann = out
         g = self.grid
         # the device emitted canonical CSR (sorted, zero-free, int32 index arrays): no conversion, no copy
         W = sp.csr_matrix((data, indices, indptr), shape=(g.n_points, g.n_elems), copy=False)

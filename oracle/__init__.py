@@ -359,6 +359,51 @@ def sample_rows(grid, method, nodes, flags, permeability=None, diff_mag=None, ne
     return weights, nws
 
 
+def gls_system_of(grid, point, flags, permeability, diff_mag, neumann_val=None):
+    """Dense GLS system [A | c] (m x (3E+1)) of ONE node exactly as build_ls_matrices / set_neumann_rows fill it
+    (gls.pyx:252-416), from any grid-like object in the reference's layouts."""
+    L = lib()
+    i8 = lambda a: np.ascontiguousarray(a, dtype=np.int64)
+    f8 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    ncol, mxf = int(grid.MX_ELEMENTS_PER_POINT), int(grid.MX_FACES_PER_POINT)
+    node = np.array([int(point)], dtype=np.int64)
+    w = np.zeros((1, ncol))
+    nw = np.zeros(1)
+    M = np.zeros((ncol + 4 * mxf) * (3 * ncol + 1))
+    mn = np.zeros(2, dtype=np.int64)
+    nval = f8(neumann_val) if neumann_val is not None else np.zeros(grid.n_points)
+    dgels, dgemv = _blas_lapack_pointers()
+    L.orc_gls_nodes.restype = ctypes.c_int
+    # the big arrays are passed as they are when already in the reference's dtypes (no copy per call)
+    L.orc_gls_nodes(_ll(1), _p(node), _ll(ncol), _ll(mxf), _p(i8(grid.esup_ptr)), _p(i8(grid.esup)), _p(i8(grid.fsup_ptr)),
+                    _p(i8(grid.fsup)), _p(i8(grid.esuf_ptr)), _p(i8(grid.esuf)), _p(i8(grid.inpofa)), _p(i8(grid.boundary_faces)),
+                    _p(i8(grid.boundary_points)), _p(i8(flags)), _p(nval), _p(f8(grid.point_coords)), _p(f8(grid.centroids)),
+                    _p(f8(grid.faces_centers)), _p(f8(grid.normal_faces)), _p(f8(np.reshape(permeability, (-1, 9)))),
+                    _p(f8(diff_mag)), dgels, dgemv, _p(w), _p(nw), _ll(int(point)), _p(M), _p(mn))
+    m, n = int(mn[0]), int(mn[1])
+    return M[:m * n].reshape(m, n), w[0], float(nw[0])
+
+
+def gls_exact_row(M, n_elem, is_neumann):
+    """The CSR row the reference's algebra defines for the system M = [A | c], evaluated in extended precision:
+    weights_i = r_i / sum_j r_j with r = c - A argmin|A g - c| (the last row of DGELS's X), plus the
+    neumann value (weight of the last element, Q3) added to every entry (Q4).  float64 QR as the preconditioner of an
+    iterative refinement whose residuals are accumulated in x87 long double (64-bit mantissa): converges to the exact
+    least-squares solution of the float64 system as long as cond(A) * 2^-53 << 1.  Used to tell which of two float64
+    answers that differ by more than the parity bar is the accurate one."""
+    A64, c64 = M[:, :-1], M[:, -1]
+    A, c = A64.astype(np.longdouble), c64.astype(np.longdouble)
+    Q, R = np.linalg.qr(A64)
+    g = np.zeros(A.shape[1], dtype=np.longdouble)
+    for _ in range(8):
+        r = c - A @ g
+        g = g + np.linalg.solve(R, Q.T @ r.astype(np.float64)).astype(np.longdouble)
+    r = (c - A @ g)[:n_elem]
+    w = r / r.sum()
+    nv = w[n_elem - 1] if is_neumann else np.longdouble(0)
+    return (w + nv).astype(np.float64), float(nv)
+
+
 def sample_csr_rows(grid, nodes, weights, nws):
     """interpolator.pyx:598-624 for the sampled rows: data = weights + neumann_ws in esup order, exact zeros
     dropped.  Returns a list of (indices int64, data float64) per sampled node."""

@@ -184,26 +184,71 @@ def test_gls_general_fronts_only(kind, n, kw, monkeypatch):
 @pytest.mark.parametrize("kind,n,kw,chunks", [("tet", 9, {"scramble": True}, 4), ("mixed", 10, {"a": 2, "b": 5}, 7),
                                               ("hex", 8, {}, 3), ("tet", 12, {}, 64), ("tet", 1, {}, 8)])
 def test_streamed_pipeline_is_bit_identical(kind, n, kw, chunks):
-    """npb_interpolate_streamed (node chunks; uploads / kernels / downloads on three streams) returns
-    exactly what count + fetch return, with the cell fields streamed in and with them resident."""
+    """The default path — npb_interpolate_run: optimistic row plan, node chunks, uploads / kernels / downloads on
+    separate streams, pooled page-locked outputs — returns exactly what the plain count + fetch path returns, with
+    the cell fields streamed in and with them resident, and with pageable inputs / outputs as well."""
     import ninpol_b200
     from ninpol_b200 import meshgen
     mesh = meshgen.make_case(kind, n, **kw)
-    I = ninpol_b200.Interpolator()
+    I = ninpol_b200.Interpolator(pinned_outputs=False, pin_inputs=False, stream_chunks=0)   # plain two-pass path
     I.load_mesh(mesh_obj=mesh)
-    J = ninpol_b200.Interpolator(pinned_outputs=True, pin_inputs=True, stream_chunks=chunks)
+    J = ninpol_b200.Interpolator(stream_chunks=chunks)
     J.load_mesh(mesh_obj=mesh)
+    P = ninpol_b200.Interpolator(pinned_outputs=False, pin_inputs=False, stream_chunks=chunks)   # pipeline, pageable host memory
+    P.load_mesh(mesh_obj=mesh)
     for method in ("gls", "idw", "ls", "gls"):
         W, nv = I.interpolate("u", method)
-        for resident in (False, True):
-            if not resident:
-                J.invalidate_inputs()
-            W2, nv2 = J.interpolate("u", method)
-            assert "streamed_ms" in J.last_timings
-            assert W2.shape == W.shape and W2.indptr.dtype == np.int32 and W2.indices.dtype == np.int32
-            assert np.array_equal(W.indptr, W2.indptr) and np.array_equal(W.indices, W2.indices)
-            assert np.array_equal(W.data, W2.data, equal_nan=True)
-            assert np.array_equal(nv, nv2, equal_nan=True)
+        assert "streamed_ms" not in I.last_timings
+        for K in (J, P):
+            for resident in (False, True):
+                if not resident:
+                    K.invalidate_inputs()
+                W2, nv2 = K.interpolate("u", method)
+                assert W2.shape == W.shape and W2.indptr.dtype == np.int32 and W2.indices.dtype == np.int32
+                assert np.array_equal(W.indptr, W2.indptr) and np.array_equal(W.indices, W2.indices)
+                assert np.array_equal(W.data, W2.data, equal_nan=True)
+                assert np.array_equal(nv, nv2, equal_nan=True)
+
+
+def test_results_are_never_overwritten_while_referenced():
+    """Drop-in semantics of the pooled page-locked outputs: a result the caller still holds survives later
+    interpolate() calls untouched; a dropped one gives its buffers back (no growth in a steady loop)."""
+    import ninpol_b200
+    from ninpol_b200 import meshgen
+    I = ninpol_b200.Interpolator()
+    I.load_mesh(mesh_obj=meshgen.make_case("tet", 8))
+    W1, n1 = I.interpolate("u", "gls")
+    keep = (W1.indptr.copy(), W1.indices.copy(), W1.data.copy(), n1.copy())
+    W2, n2 = I.interpolate("u", "idw")
+    W3, n3 = I.interpolate("u", "ls")
+    for a, b in zip((W1.indptr, W1.indices, W1.data, n1), keep):
+        assert np.array_equal(a, b)
+    assert not np.array_equal(W2.data, W3.data)
+    del W2, n2, W3, n3
+    for _ in range(4):
+        W, nv = I.interpolate("u", "idw")
+        del W, nv
+    assert max(len(v) for v in I._pool._blocks.values()) <= 3
+    assert np.array_equal(W1.data, keep[2])
+
+
+def test_exact_zero_weights_void_the_plan_and_fall_back():
+    """LS on an unperturbed hex box with Neumann hull nodes produces exact-zero weights (dropped by scipy's
+    eliminate_zeros, interpolator.pyx:624): the planned single-pass result is discarded and the two-pass path
+    answers — bit-identical to the oracle either way."""
+    import ninpol_b200
+    import oracle
+    from ninpol_b200 import meshgen
+    mesh = meshgen.make_case("hex", 10)
+    I = ninpol_b200.Interpolator()
+    I.load_mesh(mesh_obj=mesh)
+    O = oracle.OracleInterpolator().load_mesh(mesh)
+    W, nv = I.interpolate("u", "ls")
+    Wo, nvo = O.interpolate("u", "ls")
+    assert W.nnz < int(I._ctx.scalar("len_esup"))
+    assert "streamed_ms" not in I.last_timings or I.last_timings.get("k3_fill_ms", 0) >= 0
+    assert np.array_equal(W.indptr, Wo.indptr) and np.array_equal(W.indices, Wo.indices)
+    assert np.array_equal(W.data, Wo.data, equal_nan=True)
 
 
 def test_flag_truncation_matches_astype_int():

@@ -88,6 +88,7 @@ class _HostOnly:
         obj.variable_to_index = {"points": {}, "cells": {}, "faces": {}}
         obj._rows = {"cells": [], "points": []}
         obj._dense = {"cells": None, "points": None}
+        obj._data_version, obj._staged = 0, None
         return obj
 
 
@@ -188,7 +189,7 @@ def test_bench_reference_arm_prints_the_contract_line():
     import subprocess
     import sys
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                        "--ref-n", "5"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                        "--ref-workload", "tet7"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -230,3 +231,34 @@ def test_shared_outputs_mapping_is_shared_and_disappears(tmp_path, monkeypatch):
     assert W.data[0] == 42.0 and W.data.shape == (3,)
     offs = [a.off_indptr, a.off_neumann, a.off_indices, a.off_data, a.nbytes]
     assert offs == sorted(offs) and all(o % 4096 == 0 for o in offs)
+
+
+def test_pinned_pool_reuses_a_block_only_when_unreferenced(monkeypatch):
+    """_PinnedPool (the default output buffers of interpolate()): drop-in semantics need that a result the caller
+    still holds is never overwritten; a steady loop must not allocate."""
+    from ninpol_b200 import _capi, interpolator
+    allocs = []
+
+    def fake_pinned_empty(n, dtype):
+        allocs.append(n)
+        return np.empty(n, dtype)
+
+    monkeypatch.setattr(_capi, "pinned_empty", fake_pinned_empty)
+    P = interpolator._PinnedPool()
+    a = P.take("data", 100, np.float64)
+    a[:] = 1.0
+    b = P.take("data", 100, np.float64)          # a is alive: a second block
+    b[:] = 2.0
+    assert len(allocs) == 2 and a[0] == 1.0
+    del a
+    c = P.take("data", 90, np.float64)           # a's block is free again
+    assert len(allocs) == 2
+    v = c[3:7]                                   # a view of a view keeps the block busy
+    del c
+    d = P.take("data", 100, np.float64)
+    assert len(allocs) == 3 and v.base is not None
+    del b, d, v
+    for _ in range(5):                           # steady state: no growth
+        e = P.take("data", 100, np.float64)
+        del e
+    assert len(allocs) == 3

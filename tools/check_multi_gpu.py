@@ -19,6 +19,7 @@ from ninpol_b200 import dist, meshgen
 comm = dist.init_from_env()
 ok = True
 I = ninpol_b200.Interpolator(comm=comm)      # one NCCL communicator per unique id: reuse the object
+big = "--big" in sys.argv                    # adds a > 100k-node mesh (Kuhn n = 48: 117,649 nodes)
 
 
 def rows_of(W, lo, hi):
@@ -26,15 +27,22 @@ def rows_of(W, lo, hi):
     return W.indptr[lo:hi + 1] - a, W.indices[a:b], W.data[a:b]
 
 
-for kind, n, kw in (("tet", 10, {}), ("mixed", 10, {"a": 2, "b": 5}), ("hex", 12, {}), ("tet", 8, {"scramble": True})):
+CASES = [("tet", 10, {}), ("mixed", 10, {"a": 2, "b": 5}), ("hex", 12, {}), ("tet", 8, {"scramble": True})]
+if big:
+    CASES.append(("tet", 48, {}))
+for kind, n, kw in CASES:
     mesh = meshgen.make_case(kind, n, **kw)
     I.load_mesh(mesh_obj=mesh)
-    O = oracle.OracleInterpolator().load_mesh(mesh)
-    for gather in ("all", "root", "host"):
+    O = oracle.OracleInterpolator().load_mesh(mesh, build_psup=False)
+    ref = {m: O.interpolate("u", m) for m in ("idw", "ls", "gls")}
+    # chunks = 0: plain count + fetch (two-pass, counts all-gathered); 3 / 8: the planned chunk pipeline
+    for gather, chunks in (("all", 8), ("all", 0), ("root", 8), ("host", 3), ("host", 0)):
         I.set_gather(gather)
+        I.stream_chunks = chunks
         for method in ("idw", "ls", "gls"):
+            I.invalidate_inputs()
             W, nv = I.interpolate("u", method)
-            Wo, nvo = O.interpolate("u", method)
+            Wo, nvo = ref[method]
             bounds = [int(b) for b in I.partition_bounds]
             lo, hi = (0, W.shape[0]) if (gather in ("all", "host") or comm.rank == 0) else (bounds[comm.rank], bounds[comm.rank + 1])
             ip, ix, dt = rows_of(W, lo, hi)
@@ -48,7 +56,7 @@ for kind, n, kw in (("tet", 10, {}), ("mixed", 10, {"a": 2, "b": 5}), ("hex", 12
                 good = same and err <= 1e-12 and np.allclose(nv, nvo, rtol=0, atol=1e-12 * max(1.0, np.abs(nvo).max()))
             else:
                 good = same and np.array_equal(dt, dto, equal_nan=True) and np.array_equal(nv, nvo)
-            print(f"rank {comm.rank}/{comm.world} {kind}{n}{'s' if kw.get('scramble') else ''} gather={gather} {method}: "
+            print(f"rank {comm.rank}/{comm.world} {kind}{n}{'s' if kw.get('scramble') else ''} gather={gather} chunks={chunks} {method}: "
                   f"{'OK' if good else 'MISMATCH'} nnz {W.nnz} rows [{lo},{hi}) bounds {bounds}", flush=True)
             ok = ok and good
 sys.exit(0 if ok else 1)
