@@ -308,6 +308,8 @@ def timed_device_steps(I, plumb, method, steps, warmup, sampler=None):
 
 
 def timed_e2e_steps(I, plumb, method, steps, warmup):
+    # warmup >= 2: the loop below holds the previous result while the next one is computed, so the pooled page-locked
+    # output buffers ping-pong between two sets; both must exist before the clock starts (cudaHostAlloc of 2.5 GB ~ 1 s)
     def one():
         I.invalidate_inputs()
         return I.interpolate(VARIABLE, method)
@@ -389,7 +391,7 @@ def run_config(I_kwargs, comm, plumb, key, workload, methods, neumann_rate, step
         m = {"value": g.n_points / (r["ms_per_step"] * 1e-3), "unit": "nodes/s", "ms_per_step": r["ms_per_step"],
              "kernel_ms": r["kernel_ms"], "nnz": nnz, "gpu_launches": r["launches"],
              "roofline": {k: roof[k] for k in ("bound", "kernel", "achieved", "peak", "unit", "frac", "algorithmic_bytes_per_launch")}}
-        e2e_s, h2d, d2h, _n = timed_e2e_steps(I, plumb, method, steps, 1)
+        e2e_s, h2d, d2h, _n = timed_e2e_steps(I, plumb, method, steps, 2)
         m["e2e"] = {"value": g.n_points / e2e_s, "unit": "nodes/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h}
         out["methods"][method] = m
@@ -454,7 +456,7 @@ def run_ours(args, rank, world):
                                 "one 1-int exchange per step tells every rank that no plan was voided)"}
     # ---- e2e through the public API, host buffers ----
     I.set_gather(e2e_gather)
-    e2e_s, h2d, d2h, _n = timed_e2e_steps(I, plumb, method, args.steps, 1)
+    e2e_s, h2d, d2h, _n = timed_e2e_steps(I, plumb, method, args.steps, 2)
     e2e = {"value": n_points / e2e_s, "unit": "nodes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": e2e_s * 1e3,
            "api": (f"Interpolator({'comm=comm, gather=' + repr(e2e_gather) if world > 1 else ''}).interpolate(variable, method) after "
@@ -466,7 +468,7 @@ def run_ours(args, rank, world):
     e2e_all = None
     if world > 1 and e2e_gather != "all":
         I.set_gather("all")
-        s2, h2, d2, _n = timed_e2e_steps(I, plumb, method, max(2, args.steps // 4), 1)
+        s2, h2, d2, _n = timed_e2e_steps(I, plumb, method, max(2, args.steps // 4), 2)
         e2e_all = {"value": n_points / s2, "unit": "nodes/s", "ms_per_step": s2 * 1e3, "h2d_bytes_per_step": h2, "d2h_bytes_per_step": d2,
                    "api": "same, gather='all' (the constructor default): NCCL all-gather of the blocks, every rank returns the full CSR"}
         I.set_gather(e2e_gather)

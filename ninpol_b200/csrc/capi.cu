@@ -31,8 +31,9 @@ extern "C" int npb_device_count(int *count)
 int npb_alloc(npb_ctx *c, void **p, size_t bytes, bool owned_by_mesh)
 {
     *p = nullptr;
-    if (bytes == 0) bytes = 8;
-    NPB_CUDA(cudaMalloc(p, bytes));
+    // 64 bytes of slack: TMA bulk copies of element-aligned slices are rounded out to 16-byte boundaries
+    // (k2_tile_pipe.cu) and may read up to 15 bytes past the last element
+    NPB_CUDA(cudaMalloc(p, bytes + 64));
     if (owned_by_mesh) c->owned.push_back(*p);
     return NPB_OK;
 }
@@ -207,6 +208,7 @@ static void free_mesh(npb_ctx *c)
     c->counted = false;
     c->plan_kind = 0;
     c->plan_chunks = 0;
+    c->plan_failed[0] = c->plan_failed[1] = c->plan_failed[2] = false;
 }
 
 extern "C" int npb_create(int device, npb_ctx **out)
@@ -562,6 +564,7 @@ extern "C" int npb_set_cell_field(npb_ctx *c, const char *name, const double *da
     }
     NPB_CUDA(cudaStreamSynchronize(c->stream));
     c->counted = false;
+    c->plan_failed[NPB_METHOD_GLS] = false;
     return NPB_OK;
 }
 
@@ -593,6 +596,7 @@ extern "C" int npb_set_cell_field_range(npb_ctx *c, const char *name, const doub
     }
     NPB_CUDA(cudaStreamSynchronize(c->stream));
     c->counted = false;
+    c->plan_failed[NPB_METHOD_GLS] = false;
     return NPB_OK;
 }
 
@@ -625,6 +629,7 @@ extern "C" int npb_set_point_flags(npb_ctx *c, const int64_t *flag, int64_t n_po
     c->have_flags = true;
     c->counted = false;
     c->plan_kind = 0;     // row lengths depend on the flags
+    c->plan_failed[0] = c->plan_failed[1] = c->plan_failed[2] = false;
     c->fused_failed[0] = c->fused_failed[1] = false;
     return NPB_OK;
 }
@@ -659,6 +664,7 @@ extern "C" int npb_set_point_flags_f64(npb_ctx *c, const double *flag, int64_t n
     c->have_flags = true;
     c->counted = false;
     c->plan_kind = 0;     // row lengths depend on the flags
+    c->plan_failed[0] = c->plan_failed[1] = c->plan_failed[2] = false;
     c->fused_failed[0] = c->fused_failed[1] = false;
     return NPB_OK;
 }

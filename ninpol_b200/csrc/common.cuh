@@ -126,6 +126,8 @@ struct npb_ctx {
     std::vector<cudaEvent_t> pipe_ev;
     // pipeline.cu: the optimistic row plan (c->indptr holds it while plan_kind != 0: 1 = IDW / LS, 2 = GLS)
     int plan_kind = 0;
+    bool plan_failed[3] = {false, false, false};   // per method: an exact zero voided the plan for the current inputs (every
+                                                   // rank saw the same verdict), so the next call goes straight to two passes
     i64 plan_nnz = 0;
     int plan_chunks = 0;                 // chunk table below is valid for this many chunks per rank
     std::vector<i64> chunk_node, chunk_nz;   // [world * K + 1] node / nnz boundaries of every rank's chunks

@@ -332,9 +332,9 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
             const double *xs = a.fcent + (i64)face * 3;
             double N0 = Nn[0], N1 = Nn[1], N2 = Nn[2];
             double t0 = xv0 - xs[0], t1 = xv1 - xs[1], t2 = xv2 - xs[2];                     // T1 = x_v - x_S
-            double c0 = N1 * t2 - N2 * t1, c1 = N2 * t0 - N0 * t2, c2 = N0 * t1 - N1 * t0;    // T2 = N x T1
+            double c0 = gls_cross(N1, t2, N2, t1), c1 = gls_cross(N2, t0, N0, t2), c2 = gls_cross(N0, t1, N1, t0);   // T2 = N x T1
             double eta = fmax(fmax(0.0, a.diff_mag[e2.x]), a.diff_mag[e2.y]);
-            double tau = pow(sqrt(c0 * c0 + c1 * c1 + c2 * c2), -eta);
+            double tau = pow(gls_norm3(c0, c1, c2), -eta);
             const double *K1 = a.perm + (i64)e2.x * 9;
             const double *K2 = a.perm + (i64)e2.y * 9;
             // columns in ascending block order: the owner (smaller element id) has the smaller local index
@@ -343,14 +343,15 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
             if (I2 < I1) { lo_i = I2; hi_i = I1; s1 = 1.0; s2 = -1.0; const double *t = K1; K1 = K2; K2 = t; }
             double *r1 = w.arena + off_if + 21 * j;   // 3 rows x (3 + 3 + rhs)
             double *r2 = r1 + 7, *r3 = r2 + 7;
+            const double tc0 = __dmul_rn(tau, c0), tc1 = __dmul_rn(tau, c1), tc2 = __dmul_rn(tau, c2);
 #pragma unroll
             for (int q = 0; q < 3; q++) {
-                r1[q] = s1 * (K1[3 * q] * N0 + K1[3 * q + 1] * N1 + K1[3 * q + 2] * N2);
-                r1[3 + q] = s2 * (K2[3 * q] * N0 + K2[3 * q + 1] * N1 + K2[3 * q + 2] * N2);
+                r1[q] = s1 * gls_kn(K1 + 3 * q, N0, N1, N2);
+                r1[3 + q] = s2 * gls_kn(K2 + 3 * q, N0, N1, N2);
             }
             r2[0] = s1 * t0; r2[1] = s1 * t1; r2[2] = s1 * t2; r2[3] = s2 * t0; r2[4] = s2 * t1; r2[5] = s2 * t2;
-            r3[0] = s1 * (tau * c0); r3[1] = s1 * (tau * c1); r3[2] = s1 * (tau * c2);
-            r3[3] = s2 * (tau * c0); r3[4] = s2 * (tau * c1); r3[5] = s2 * (tau * c2);
+            r3[0] = s1 * tc0; r3[1] = s1 * tc1; r3[2] = s1 * tc2;
+            r3[3] = s2 * tc0; r3[4] = s2 * tc1; r3[5] = s2 * tc2;
             r1[6] = 0.0; r2[6] = 0.0; r3[6] = 0.0;
             int g = E + j;
             w.g_mask[g] = (1ull << lo_i) | (1ull << hi_i);
@@ -368,7 +369,7 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
             double N0 = Nn[0], N1 = Nn[1], N2 = Nn[2];
             double *rr = w.arena + off_bf + 4 * j;
 #pragma unroll
-            for (int q = 0; q < 3; q++) rr[q] = -(K1[3 * q] * N0 + K1[3 * q + 1] * N1 + K1[3 * q + 2] * N2);
+            for (int q = 0; q < 3; q++) rr[q] = -gls_kn(K1 + 3 * q, N0, N1, N2);
             rr[3] = 0.0;
             int g = E + n_if + j;
             w.g_mask[g] = 1ull << Ik;

@@ -76,9 +76,9 @@ __device__ void gls_node_dense(const GlsArgs &a, int p, double *ws)
             const double *xs = a.fcent + (i64)face * 3;
             double N0 = Nn[0], N1 = Nn[1], N2 = Nn[2];
             double t0 = xv0 - xs[0], t1 = xv1 - xs[1], t2 = xv2 - xs[2];
-            double c0 = N1 * t2 - N2 * t1, c1 = N2 * t0 - N0 * t2, c2 = N0 * t1 - N1 * t0;
+            double c0 = gls_cross(N1, t2, N2, t1), c1 = gls_cross(N2, t0, N0, t2), c2 = gls_cross(N0, t1, N1, t0);
             double eta = fmax(fmax(0.0, a.diff_mag[e2.x]), a.diff_mag[e2.y]);
-            double tau = pow(sqrt(c0 * c0 + c1 * c1 + c2 * c2), -eta);
+            double tau = pow(gls_norm3(c0, c1, c2), -eta);
             const double *K1 = a.perm + (i64)e2.x * 9;
             const double *K2 = a.perm + (i64)e2.y * 9;
             double *r1 = M + (size_t)(E + 3 * j) * ld;
@@ -86,15 +86,16 @@ __device__ void gls_node_dense(const GlsArgs &a, int p, double *ws)
             double *r3 = r2 + ld;
 #pragma unroll
             for (int q = 0; q < 3; q++) {
-                double k1n = K1[3 * q] * N0 + K1[3 * q + 1] * N1 + K1[3 * q + 2] * N2;
-                double k2n = K2[3 * q] * N0 + K2[3 * q + 1] * N1 + K2[3 * q + 2] * N2;
+                double k1n = gls_kn(K1 + 3 * q, N0, N1, N2);
+                double k2n = gls_kn(K2 + 3 * q, N0, N1, N2);
                 r1[3 * I1 + q] = -k1n;
                 r1[3 * I2 + q] = k2n;
             }
             r2[3 * I1 + 0] = -t0; r2[3 * I1 + 1] = -t1; r2[3 * I1 + 2] = -t2;
             r2[3 * I2 + 0] = t0;  r2[3 * I2 + 1] = t1;  r2[3 * I2 + 2] = t2;
-            r3[3 * I1 + 0] = -(tau * c0); r3[3 * I1 + 1] = -(tau * c1); r3[3 * I1 + 2] = -(tau * c2);
-            r3[3 * I2 + 0] = tau * c0;    r3[3 * I2 + 1] = tau * c1;    r3[3 * I2 + 2] = tau * c2;
+            const double tc0 = __dmul_rn(tau, c0), tc1 = __dmul_rn(tau, c1), tc2 = __dmul_rn(tau, c2);
+            r3[3 * I1 + 0] = -tc0; r3[3 * I1 + 1] = -tc1; r3[3 * I1 + 2] = -tc2;
+            r3[3 * I2 + 0] = tc0;  r3[3 * I2 + 1] = tc1;  r3[3 * I2 + 2] = tc2;
         }
         if (boundary && neu) {
             int j = bf_seen + __popc(mb & below);
@@ -106,7 +107,7 @@ __device__ void gls_node_dense(const GlsArgs &a, int p, double *ws)
             double N0 = Nn[0], N1 = Nn[1], N2 = Nn[2];
             double *rr = M + (size_t)(E + 3 * n_if + j) * ld;
 #pragma unroll
-            for (int q = 0; q < 3; q++) rr[3 * Ik + q] = -(K1[3 * q] * N0 + K1[3 * q + 1] * N1 + K1[3 * q + 2] * N2);
+            for (int q = 0; q < 3; q++) rr[3 * Ik + q] = -gls_kn(K1 + 3 * q, N0, N1, N2);
         }
         if_seen += __popc(mi);
         bf_seen += __popc(mb);

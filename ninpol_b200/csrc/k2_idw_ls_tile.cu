@@ -18,6 +18,7 @@
 // takes the general two-pass path (k2_idw_ls.cu + k3_emit.cu).
 #include <stdlib.h>
 #include "common.cuh"
+#include "tile_args.cuh"
 
 #define TILE_NB 64
 #define TILE_T 256
@@ -54,22 +55,6 @@ __global__ void k_row_plan(const int32_t *__restrict__ esup_ptr, const uint8_t *
     neumann[p] = 0.0;
 }
 
-struct TileArgs {
-    const int32_t *esup_ptr, *esup;
-    const uint8_t *bpoint, *nflag;
-    const double *coords, *cent;
-    const int32_t *indptr;
-    int32_t *indices;
-    double *data;
-    int *zero_counter;
-    double *neumann;
-    double *wbuf;        // two-pass mode: values go to wbuf (esup-indexed from wbase) and rowcnt[p] = surviving entries
-    int32_t *rowcnt;
-    i64 wbase;
-    i64 p_lo, p_hi;      // node range of this launch
-    int nb, dim;
-    int direct;          // 1: write the CSR at indptr[] positions and count exact zeros; 0: two-pass mode
-};
 
 template <int NBCAP>
 __global__ void __launch_bounds__(TILE_T, 7) k_idw_tile(TileArgs a)
@@ -326,7 +311,10 @@ static int tile_launch(npb_ctx *c, const TileArgs &a, int method)
     int grid = (int)(ntiles < (i64)c->sm_count * 8 ? ntiles : (i64)c->sm_count * 8);
     if (grid < 1) return NPB_OK;
     NpbTimer tm(c, "k2_main");
-    if (method == NPB_METHOD_IDW) {
+    int piped = 0;
+    NPB_TRY(npb_tile_pipe_launch(c, a, method, &piped));
+    if (piped) {
+    } else if (method == NPB_METHOD_IDW) {
         k_idw_tile<TILE_NB><<<grid, TILE_T, 0, c->stream>>>(a);
     } else {
         if (a.nb > TILE_NB)

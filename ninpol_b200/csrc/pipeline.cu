@@ -284,6 +284,7 @@ static int run_pipeline(npb_ctx *c, int method, int K, const double *perm_host, 
     if (W > 1) NPB_TRY(npb_k4_share_flags(c, mine, &any));
     if (any) {
         *fell_back = 1;
+        c->plan_failed[method] = true;
         c->plan_kind = 0;   // the two-pass path rewrites indptr
         return NPB_OK;
     }
@@ -333,6 +334,11 @@ extern "C" int npb_interpolate_run(npb_ctx *c, int method, int n_chunks, const d
     NPB_CUDA(cudaSetDevice(c->device));
     if (n_chunks < 1) n_chunks = 1;
     if (n_chunks > 64) n_chunks = 64;
+    if (c->plan_failed[method]) {   // same inputs -> same zeros: do not compute a result that will be discarded again
+        *fell_back = 1;
+        *nnz = 0;
+        return NPB_OK;
+    }
     NpbTimer tall(c, "streamed");
     int rc = run_pipeline(c, method, n_chunks, perm_host, diff_mag_host, indptr, indices, data, neumann, capacity, fell_back);
     if (rc != NPB_OK) {
