@@ -82,6 +82,59 @@ __global__ void k_sort_rows(const int32_t *__restrict__ ptr, i64 n_rows, int32_t
     if ((threadIdx.x & 31) == 0 && len > 0) atomicMax(mx, len);
 }
 
+// The same sort with the rows of a CTA staged in shared memory: SORT_ROWS consecutive rows are one contiguous slice of
+// `vals`, so it is read and written back fully coalesced (TMA-friendly layout) and the per-row insertion sort — rows
+// arrive almost sorted, because element / face ids grow with the launch order of the atomic fill — runs on shared
+// memory instead of on scattered global words.  Slices larger than the buffer fall back to the in-place sort.
+#define SORT_ROWS 256
+#define SORT_CAP 12032   // ints of shared memory (47 KB): 256 rows of up to 47 entries
+__global__ void __launch_bounds__(SORT_ROWS)
+k_sort_rows_smem(const int32_t *__restrict__ ptr, i64 n_rows, int32_t *__restrict__ vals, int *__restrict__ mx)
+{
+    __shared__ int32_t buf[SORT_CAP];
+    const i64 r0 = (i64)blockIdx.x * SORT_ROWS;
+    const i64 r1 = min(r0 + SORT_ROWS, n_rows);
+    const i64 r = r0 + threadIdx.x;
+    const int b0 = ptr[r0], b1 = ptr[r1];
+    const int ne = b1 - b0;
+    int len = 0;
+    if (ne <= SORT_CAP) {
+        for (int i = threadIdx.x; i < ne; i += SORT_ROWS) buf[i] = vals[(i64)b0 + i];
+        __syncthreads();
+        if (r < r1) {
+            const int b = ptr[r] - b0;
+            len = ptr[r + 1] - ptr[r];
+            int32_t *row = buf + b;
+            for (int i = 1; i < len; i++) {
+                int32_t v = row[i];
+                int j = i - 1;
+                while (j >= 0 && row[j] > v) {
+                    row[j + 1] = row[j];
+                    j--;
+                }
+                row[j + 1] = v;
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < ne; i += SORT_ROWS) vals[(i64)b0 + i] = buf[i];
+    } else if (r < r1) {
+        i64 b = ptr[r];
+        len = ptr[r + 1] - ptr[r];
+        int32_t *row = vals + b;
+        for (int i = 1; i < len; i++) {
+            int32_t v = row[i];
+            int j = i - 1;
+            while (j >= 0 && row[j] > v) {
+                row[j + 1] = row[j];
+                j--;
+            }
+            row[j + 1] = v;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+    if ((threadIdx.x & 31) == 0 && len > 0) atomicMax(mx, len);
+}
+
 // ------------------------------------------------------------------------------------------------
 // esuel: one thread per (element, local face).  Candidates are the elements around the face's
 // lowest-degree node (first minimum in local order, grid.pyx:479-488); a candidate matches when one of
@@ -129,31 +182,41 @@ k_esuel(ElemTables tab, FaceMasks fm, const int32_t *__restrict__ inpoel, const 
     }
     int res = -1;
     const int qb = esup_ptr[point], qe = esup_ptr[point + 1];
-    for (int q = qb; q < qe; q++) {
-        int je = esup[q];
-        if (je == (int)e) continue;
-        int row[SPE];
-        const int4 *rp = reinterpret_cast<const int4 *>(inpoel + (i64)je * SPE);
+    // candidates in batches of CB: the ids, then the connectivity rows, are fetched with independent loads before any
+    // of them is examined (one dependent round trip per batch instead of two per candidate); first match in esup order
+    constexpr int CB = 4;
+    for (int q0 = qb; q0 < qe && res < 0; q0 += CB) {
+        int cand[CB];
 #pragma unroll
-        for (int v = 0; v < SPE / 4; v++) {
-            int4 x = rp[v];
-            row[4 * v] = x.x; row[4 * v + 1] = x.y; row[4 * v + 2] = x.z; row[4 * v + 3] = x.w;
-        }
-        unsigned hit = 0;
+        for (int u = 0; u < CB; u++) cand[u] = (q0 + u < qe) ? esup[q0 + u] : -1;
+        int4 rows[CB][SPE / 4];
 #pragma unroll
-        for (int k = 0; k < SPE; k++) {
-            int qn = row[k];
-            bool h = (qn == mine[0]) | (qn == mine[1]) | (qn == mine[2]) | (qn == mine[3]);
-            hit |= h ? (1u << k) : 0u;
+        for (int u = 0; u < CB; u++) {
+            const int4 *rp = reinterpret_cast<const int4 *>(inpoel + (i64)(cand[u] < 0 ? 0 : cand[u]) * SPE);
+#pragma unroll
+            for (int v = 0; v < SPE / 4; v++) rows[u][v] = rp[v];
         }
-        if (__popc(hit) < nj) continue;       // cannot match any face
-        int jt = etype[je];
-        int nf = tab.nfael[jt];
-        bool match = false;
-        for (int l = 0; l < nf; l++) match = match || (__popc(hit & fm.m[jt][l]) == nj);
-        if (match) {
-            res = je;
-            break;
+#pragma unroll
+        for (int u = 0; u < CB; u++) {
+            const int je = cand[u];
+            if (je < 0 || je == (int)e || res >= 0) continue;
+            unsigned hit = 0;
+#pragma unroll
+            for (int v = 0; v < SPE / 4; v++) {
+                const int4 x = rows[u][v];
+                const int qn[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    bool h = (qn[k] == mine[0]) | (qn[k] == mine[1]) | (qn[k] == mine[2]) | (qn[k] == mine[3]);
+                    hit |= h ? (1u << (4 * v + k)) : 0u;
+                }
+            }
+            if (__popc(hit) < nj) continue;       // cannot match any face
+            int jt = etype[je];
+            int nf = tab.nfael[jt];
+            bool match = false;
+            for (int l = 0; l < nf; l++) match = match || (__popc(hit & fm.m[jt][l]) == nj);
+            if (match) res = je;
         }
     }
     esuel[idx] = res;
@@ -320,7 +383,7 @@ int npb_k1_build(npb_ctx *c, const i64 *h_conn, int cstride, const i64 *h_types,
         NPB_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (np + 1), s));
         k_fill_rows<<<npb_blocks(ne * spe, T), T, 0, s>>>(c->inpoel, ne * spe, spe, c->esup_ptr, cursor, c->esup);
         NPB_LAUNCH(c);
-        k_sort_rows<<<npb_blocks(np, T), T, 0, s>>>(c->esup_ptr, np, c->esup, d_mx + 0);
+        k_sort_rows_smem<<<npb_blocks(np, SORT_ROWS), SORT_ROWS, 0, s>>>(c->esup_ptr, np, c->esup, d_mx + 0);
         NPB_LAUNCH(c);
         tm.stop();
     }
@@ -390,7 +453,7 @@ int npb_k1_build(npb_ctx *c, const i64 *h_conn, int cstride, const i64 *h_types,
         NPB_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (np + 1), s));
         k_fill_fsup<<<npb_blocks(c->n_faces * NPB_MX_PF, T), T, 0, s>>>(c->inpofa, c->n_faces, c->fsup_ptr, cursor, c->fsup);
         NPB_LAUNCH(c);
-        k_sort_rows<<<npb_blocks(np, T), T, 0, s>>>(c->fsup_ptr, np, c->fsup, d_mx + 1);
+        k_sort_rows_smem<<<npb_blocks(np, SORT_ROWS), SORT_ROWS, 0, s>>>(c->fsup_ptr, np, c->fsup, d_mx + 1);
         NPB_LAUNCH(c);
         tm.stop();
     }

@@ -60,7 +60,9 @@ struct MfClass {
 __constant__ MfClass c_mf[MF_NCLASS] = MF_CLASS_TABLE;
 static MfClass h_mf[MF_NCLASS] = MF_CLASS_TABLE;
 
-__host__ __device__ __forceinline__ int mf_ngcap(const MfClass &k) { return ((2 * k.ecap + k.fcap_f + 7) / 8) * 8; }
+// group table entries: original groups (<= ecap + fcap_f), leaf contribution blocks and re-entered survivors of the
+// leaf phase (<= ecap together), one contribution block per general front (<= ecap)
+__host__ __device__ __forceinline__ int mf_ngcap(const MfClass &k) { return ((3 * k.ecap + k.fcap_f + 7) / 8) * 8; }
 __host__ __device__ __forceinline__ size_t mf_smem_bytes(const MfClass &k)
 {
     size_t d = (size_t)k.fcap + 6 * (size_t)k.ecap;  // front, gvec, dvec
@@ -283,20 +285,12 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
     const int ngcap = mf_ngcap(kc);
 
     // ---- setup: esup row, element groups ----
+    // The original rows (element rows, face groups, Neumann rows) are built in the SHARED front buffer, which is idle
+    // until the first general front: the lane-per-leaf phase reads them from there, and only the groups it leaves
+    // behind (the element rows of the non-leaf blocks on a closed star) move on to the global arena.  Keeps ~0.85 k
+    // doubles per node out of the L2-resident slab and takes the global round trips out of the leaf phase.
     for (int i = lane; i < E; i += 32) w.es[i] = a.esup[eb + i];
     __syncwarp();
-    for (int i = lane; i < E; i += 32) {
-        const double *cc = a.cent + (i64)w.es[i] * 3;
-        double d0 = cc[0] - xv0, d1 = cc[1] - xv1, d2 = cc[2] - xv2;
-        w.dvec[3 * i] = d0; w.dvec[3 * i + 1] = d1; w.dvec[3 * i + 2] = d2;
-        double *row = w.arena + 4 * i;                    // [ d^T | 1 ]   gls.pyx:268-281
-        row[0] = d0; row[1] = d1; row[2] = d2; row[3] = 1.0;
-        w.g_mask[i] = 1ull << i;
-        w.g_off[i] = 4 * i;
-        w.g_nr[i] = 1;
-        w.g_ld[i] = 4;
-    }
-    // ---- face groups (gls.pyx:291-356) and Neumann groups (:394-416) ----
     int n_if = 0;
     for (int f0 = 0; f0 < F; f0 += 32) {
         int fi = f0 + lane;
@@ -306,6 +300,21 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
     }
     const int n_bf = F - n_if;
     const int off_if = 4 * E, off_bf = 4 * E + 21 * n_if;
+    const int orig_len = off_bf + (neu ? 4 * n_bf : 0);
+    const bool orig_in_smem = orig_len <= kc.fcap;
+    double *orig = orig_in_smem ? w.front : w.arena;
+    for (int i = lane; i < E; i += 32) {
+        const double *cc = a.cent + (i64)w.es[i] * 3;
+        double d0 = cc[0] - xv0, d1 = cc[1] - xv1, d2 = cc[2] - xv2;
+        w.dvec[3 * i] = d0; w.dvec[3 * i + 1] = d1; w.dvec[3 * i + 2] = d2;
+        double *row = orig + 4 * i;                       // [ d^T | 1 ]   gls.pyx:268-281
+        row[0] = d0; row[1] = d1; row[2] = d2; row[3] = 1.0;
+        w.g_mask[i] = 1ull << i;
+        w.g_off[i] = 4 * i;
+        w.g_nr[i] = 1;
+        w.g_ld[i] = 4;
+    }
+    // ---- face groups (gls.pyx:291-356) and Neumann groups (:394-416) ----
     int if_seen = 0, bf_seen = 0;
     for (int f0 = 0; f0 < F; f0 += 32) {
         int fi = f0 + lane;
@@ -341,7 +350,7 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
             double s1 = -1.0, s2 = 1.0;
             int lo_i = I1, hi_i = I2;
             if (I2 < I1) { lo_i = I2; hi_i = I1; s1 = 1.0; s2 = -1.0; const double *t = K1; K1 = K2; K2 = t; }
-            double *r1 = w.arena + off_if + 21 * j;   // 3 rows x (3 + 3 + rhs)
+            double *r1 = orig + off_if + 21 * j;      // 3 rows x (3 + 3 + rhs)
             double *r2 = r1 + 7, *r3 = r2 + 7;
             const double tc0 = __dmul_rn(tau, c0), tc1 = __dmul_rn(tau, c1), tc2 = __dmul_rn(tau, c2);
 #pragma unroll
@@ -367,7 +376,7 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
             const double *Nn = a.fnormal + (i64)face * 3;
             const double *K1 = a.perm + (i64)e2.x * 9;
             double N0 = Nn[0], N1 = Nn[1], N2 = Nn[2];
-            double *rr = w.arena + off_bf + 4 * j;
+            double *rr = orig + off_bf + 4 * j;
 #pragma unroll
             for (int q = 0; q < 3; q++) rr[q] = -gls_kn(K1 + 3 * q, N0, N1, N2);
             rr[3] = 0.0;
@@ -381,7 +390,8 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
         bf_seen += __popc(mb);
     }
     int ng = E + n_if + (neu ? n_bf : 0);
-    int top = off_bf + (neu ? 4 * n_bf : 0);
+    const int ng_orig = ng;
+    int top = orig_in_smem ? 0 : orig_len;   // the global arena starts empty when the original rows live in shared memory
     __syncwarp();
 
     // ---- adjacency bitmasks: lane b owns blocks b and b + 32 ----
@@ -477,7 +487,7 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
 #pragma unroll
             for (int k = 0; k < 3; k++) {
                 // own columns come second when the neighbour has the smaller index
-                const double *src = w.arena + offk[k] + ((intr[k] && nbk[k] < b) ? 3 : 0);
+                const double *src = orig + offk[k] + ((intr[k] && nbk[k] < b) ? 3 : 0);
                 const int ld = intr[k] ? 7 : 4;
 #pragma unroll
                 for (int r = 0; r < 3; r++) {
@@ -536,7 +546,7 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
             for (int k = 0; k < 3; k++) {
                 if (!intr[k]) continue;
                 const int slot = 1 + __popcll(Upl & ((1ull << nbk[k]) - 1ull));
-                const double *src = w.arena + offk[k] + ((nbk[k] < b) ? 0 : 3);
+                const double *src = orig + offk[k] + ((nbk[k] < b) ? 0 : 3);
 #pragma unroll
                 for (int q = 0; q < 3; q++) {
                     const double n0 = src[q], n1 = src[7 + q], n2 = src[14 + q];
@@ -600,6 +610,45 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
         nR += __popc(chosen);
         n_leaf = nR;
         rtop += r_tot;
+        __syncwarp();
+    }
+
+    // ---- original groups that survived the leaf phase leave the front buffer for the global arena ----
+    // They are re-entered at the END of the group table, so that table order stays arena order (mf_compact relies on it).
+    if (orig_in_smem) {
+        for (int g0 = 0; g0 < ng_orig; g0 += 32) {
+            const int g = g0 + lane;
+            int sz = 0, src_off = 0, nr = 0, gld = 0;
+            u64 mk = 0;
+            if (g < ng_orig && w.g_nr[g] > 0) {
+                nr = w.g_nr[g];
+                gld = w.g_ld[g];
+                sz = nr * gld;
+                src_off = w.g_off[g];
+                mk = w.g_mask[g];
+            }
+            int incl = sz;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int tot = __shfl_sync(FULL, incl, 31);
+            const unsigned live = __ballot_sync(FULL, sz > 0);
+            if (top + tot > kc.acap || ng + __popc(live) > ngcap) return 1;
+            if (sz > 0) {
+                const int dst = top + incl - sz;
+                for (int q = 0; q < sz; q++) w.arena[dst + q] = orig[src_off + q];
+                const int gi = ng + __popc(live & ((1u << lane) - 1u));
+                w.g_mask[gi] = mk;
+                w.g_off[gi] = dst;
+                w.g_nr[gi] = (unsigned short)nr;
+                w.g_ld[gi] = (unsigned char)gld;
+                w.g_nr[g] = 0;
+            }
+            top += tot;
+            ng += __popc(live);
+        }
         __syncwarp();
     }
 
@@ -1029,6 +1078,14 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
         part += ri;
     }
     double tot = warp_sum(part);
+    // r_i = 1 - d_i . g_i and sum_i r_i lose digits to cancellation when the system is nearly consistent (residuals
+    // << 1, or of mixed sign: one-sided stars, typically 2-D Neumann boundary nodes; in 3-D r_i ~ 1 and the statistic
+    // below sits at 2).  Such nodes go to the dense kernel, which forms r through the reflectors (k2_gls_dense.cu).
+    double rmx = 0.0;
+    for (int i = lane; i < E; i += 32) rmx = fmax(rmx, fabs(w.front[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rmx = fmax(rmx, __shfl_xor_sync(FULL, rmx, o));
+    if (!(1.0 / rmx + (double)E / fabs(tot) <= 8.0)) return 1;
     __syncwarp();
     double nv = neu ? w.front[E - 1] / tot : 0.0;   // gls.pyx:470-472 (Q3)
     int cnt = 0;

@@ -7,8 +7,8 @@
 
 __host__ __device__ __forceinline__ size_t gls_dense_ws_bytes(int E, int m)
 {
-    // M [m, 3E+1] + vv [m] + rinv/g [3E+1] doubles, then es [E] ints (padded to 8 bytes)
-    size_t d = (size_t)m * (3 * E + 1) + m + (3 * E + 1);
+    // M [m, 3E+1] + vv [m] + vdiag [3E+1] + beta [3E+1] doubles, then es [E] ints (padded to 8 bytes)
+    size_t d = (size_t)m * (3 * E + 1) + m + 2 * (size_t)(3 * E + 1);
     return d * 8 + (((size_t)E * 4 + 7) & ~(size_t)7);
 }
 
@@ -33,8 +33,9 @@ __device__ void gls_node_dense(const GlsArgs &a, int p, double *ws)
 
     double *M = ws;
     double *vv = M + (size_t)m * ld;
-    double *gg = vv + m;             // [ld]: reciprocal diagonal, then the solution g
-    int *es = (int *)(gg + ld);      // [E]: the node's esup row
+    double *vd = vv + m;             // [ld]: v_k[k] = x_k - alpha_k (the sub-diagonal part of v_k stays in column k of M)
+    double *bt = vd + ld;            // [ld]: beta_k = 2 / |v_k|^2 (0 for a zero column)
+    int *es = (int *)(bt + ld);      // [E]: the node's esup row
 
     for (int i = lane; i < m * ld; i += 32) M[i] = 0.0;
     for (int i = lane; i < E; i += 32) es[i] = a.esup[eb + i];
@@ -114,7 +115,8 @@ __device__ void gls_node_dense(const GlsArgs &a, int p, double *ws)
     }
     __syncwarp();
 
-    // Householder QR of [A | c], natural column order
+    // Householder QR of [A | c], natural column order (the order DGELS uses); the reflectors are kept: v_k below the
+    // diagonal of column k, its leading entry in vd[k], beta_k in bt[k]
     const int kmax = n < m ? n : m;
     for (int k = 0; k < kmax; k++) {
         double part = 0.0;
@@ -126,7 +128,10 @@ __device__ void gls_node_dense(const GlsArgs &a, int p, double *ws)
         double sigma = warp_sum(part);
         __syncwarp();
         if (sigma == 0.0) {
-            if (lane == 0) gg[k] = 0.0;
+            if (lane == 0) {
+                vd[k] = 0.0;
+                bt[k] = 0.0;
+            }
             continue;
         }
         double x0 = vv[k];
@@ -135,8 +140,9 @@ __device__ void gls_node_dense(const GlsArgs &a, int p, double *ws)
         __syncwarp();
         if (lane == 0) {
             vv[k] = x0 - alpha;
+            vd[k] = x0 - alpha;
+            bt[k] = beta;
             M[(size_t)k * ld + k] = alpha;
-            gg[k] = 1.0 / alpha;
         }
         __syncwarp();
         for (int j0 = k + 1; j0 < ld; j0 += 32) {
@@ -155,27 +161,35 @@ __device__ void gls_node_dense(const GlsArgs &a, int p, double *ws)
         }
         __syncwarp();
     }
-    // back substitution R g = z (column oriented; z lives in column n)
+    // The weights are the element-row entries of r / |r|^2, r = c - A g the least-squares residual.  r is formed by
+    // applying the reflectors BACKWARDS to what the factorisation left of c below the triangle, r = Q [0; z] - the
+    // route DGELS itself takes for its E right-hand sides (X[3E, i] = (Q^T e_i)[3E] / rho) - and |r|^2 = |z|^2 is a
+    // sum of squares.  Forming r as 1 - d_i . g_i from the back-substituted g, and |r|^2 as sum_i r_i, loses digits to
+    // cancellation wherever the system is nearly consistent (one-sided stars at Neumann boundary nodes: weights of
+    // +-75 on a 2-D corner, error 2e-9 instead of 1e-14).
+    double zz = 0.0;
+    for (int r = lane; r < m; r += 32) {
+        double y = (r >= kmax) ? M[(size_t)r * ld + n] : 0.0;
+        vv[r] = y;
+        zz += y * y;
+    }
+    const double rho2 = warp_sum(zz);
+    __syncwarp();
     for (int k = kmax - 1; k >= 0; k--) {
-        double gk = M[(size_t)k * ld + n] * gg[k];
+        const double beta = bt[k];
+        if (beta == 0.0) continue;     // warp-uniform
+        double part = 0.0;
+        for (int r = k + 1 + lane; r < m; r += 32) part += M[(size_t)r * ld + k] * vv[r];
+        double dot = warp_sum(part) + vd[k] * vv[k];
+        const double sc = beta * dot;
         __syncwarp();
-        if (lane == 0) gg[k] = gk;
-        for (int r = lane; r < k; r += 32) M[(size_t)r * ld + n] -= M[(size_t)r * ld + k] * gk;
+        for (int r = k + 1 + lane; r < m; r += 32) vv[r] -= sc * M[(size_t)r * ld + k];
+        if (lane == 0) vv[k] -= sc * vd[k];
         __syncwarp();
     }
-    for (int k = kmax + lane; k < n; k += 32) gg[k] = 0.0;
-    __syncwarp();
-    // residual on the element rows, weights, CSR values
+    // weights, CSR values
     double *w = a.wbuf + ((i64)eb - a.wbase);
-    double part = 0.0;
-    for (int i = lane; i < E; i += 32) {
-        const double *cc = a.cent + (i64)es[i] * 3;
-        double ri = 1.0 - ((cc[0] - xv0) * gg[3 * i] + (cc[1] - xv1) * gg[3 * i + 1] + (cc[2] - xv2) * gg[3 * i + 2]);
-        vv[i] = ri;
-        part += ri;
-    }
-    double tot = warp_sum(part);
-    __syncwarp();
+    const double tot = rho2;
     double nv = neu ? vv[E - 1] / tot : 0.0;   // gls.pyx:470-472 (Q3)
     int cnt = 0;
     for (int i = lane; i < E; i += 32) {

@@ -75,8 +75,9 @@ __device__ __forceinline__ unsigned bulk_slice(void *dst, const void *src, unsig
 template <int NB, int ECAP>
 struct PipeSmem {
     // ring of 3: contiguous slices (16-byte aligned starts; up to 15 lead bytes + 15 tail bytes of slack each)
-    alignas(16) int ptr[3][NB + 1 + 8];
-    alignas(16) int out[3][NB + 1 + 8];
+    // (every ring row is a multiple of 16 bytes: each slot is the 16-byte aligned destination of a bulk copy)
+    alignas(16) int ptr[3][(NB + 1 + 8 + 3) & ~3];
+    alignas(16) int out[3][(NB + 1 + 8 + 3) & ~3];
     alignas(16) double xyz[3][3 * NB + 4];
     alignas(16) unsigned char bp[3][NB + 32];
     alignas(16) unsigned char nf[3][NB + 32];
@@ -93,6 +94,9 @@ struct PipeSmem {
     int fz[NB], cnt[NB];
     unsigned char mode[NB], proc[NB];
 };
+
+static_assert((3 * 64 + 4) % 2 == 0 && (64 + 32) % 16 == 0 && (1408 + 8) % 4 == 0 && (1024 + 8) % 4 == 0 && (128 + 32) % 16 == 0,
+              "ring rows of PipeSmem must be multiples of 16 bytes");
 
 template <int METHOD, int NB, int ECAP, int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) k_tile_pipe(TileArgs a)

@@ -84,10 +84,14 @@ def test_c2_full_comparison_with_compiled_reference(kind, n):
                 M, _w, _n = oracle.gls_system_of(g, p, flags, perm, dm, mesh.point_data["neumann_u"])
                 return oracle.gls_exact_row(M, int(esup_ptr[p + 1] - esup_ptr[p]), bool(flags[p]) and bool(bp[p]))[0]
 
-            v = gls_verdict(W.indptr, W.data, Wr.data, exact_row)
+            try:
+                v = gls_verdict(W.indptr, W.data, Wr.data, exact_row)
+            except AssertionError as e:
+                _record(key, gls=e.args[0] if e.args and isinstance(e.args[0], dict) else str(e)[:600])
+                raise
             nerr = float(np.max(np.abs(nv - nvr))) / max(1.0, float(np.max(np.abs(nvr))))
             _record(key, gls=v, gls_neumann_abs=nerr, gls_nnz=int(W.nnz), reference_gls_s=round(t_ref, 2))
-            assert nerr <= 2e-11, nerr
+            assert nerr <= 5e-12, nerr
         else:
             assert np.array_equal(W.data, Wr.data, equal_nan=True), method
             assert np.array_equal(nv, nvr), method
@@ -152,11 +156,15 @@ def _at_size(kind, n, kw, key):
                 M, _w, _n = oracle.gls_system_of(g, p, flags, perm, dm, mesh.point_data["neumann_u"])
                 return oracle.gls_exact_row(M, int(esup_ptr[p + 1] - esup_ptr[p]), bool(flags[p]) and bool(bpoints[p]))[0]
 
-            v = gls_verdict(ptr, got, ref_dat, exact_row)
+            try:
+                v = gls_verdict(ptr, got, ref_dat, exact_row)
+            except AssertionError as e:
+                _record(key, gls=e.args[0] if e.args and isinstance(e.args[0], dict) else str(e)[:600])
+                raise
             nerr = float(np.max(np.abs(nv[nodes] - nws))) / max(1.0, float(np.max(np.abs(nws))))
             _record(key, gls=v, gls_sampled_nodes=int(len(nodes)), gls_sampled_neumann_nodes=int(n_neu), gls_neumann_abs=nerr,
                     oracle_gls_s=round(t_or, 2))
-            assert nerr <= 2e-11, nerr
+            assert nerr <= 5e-12, nerr
         else:
             assert np.array_equal(got, ref_dat, equal_nan=True), method
             assert np.array_equal(nv[nodes], nws), method
