@@ -170,7 +170,8 @@ int npb_ensure_out(npb_ctx *c, size_t n);
 int npb_k2_gls(npb_ctx *c, i64 lo, i64 hi);
 int npb_k3_fill(npb_ctx *c, i64 lo, i64 hi);
 int npb_read_int(npb_ctx *c, const int *d_src, int *h_out);
-__global__ void k_copy2_int(int *dst, const int *src);   // capi.cu: two ints, device -> mapped host block   // device int -> host through the mapped block + stream sync
+__global__ void k_copy2_int(int *dst, const int *src);   // capi.cu: two ints, device -> mapped host block
+__global__ void k_copy_int(int *dst, const int *src);    // capi.cu   // device int -> host through the mapped block + stream sync
 int npb_minmax_i32(npb_ctx *c, const int32_t *in, i64 n, int32_t *h_min, int32_t *h_max);
 int npb_k4_gather_counts(npb_ctx *c);
 int npb_k4_gather_blocks(npb_ctx *c);

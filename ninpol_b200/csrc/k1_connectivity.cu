@@ -182,41 +182,31 @@ k_esuel(ElemTables tab, FaceMasks fm, const int32_t *__restrict__ inpoel, const 
     }
     int res = -1;
     const int qb = esup_ptr[point], qe = esup_ptr[point + 1];
-    // candidates in batches of CB: the ids, then the connectivity rows, are fetched with independent loads before any
-    // of them is examined (one dependent round trip per batch instead of two per candidate); first match in esup order
-    constexpr int CB = 4;
-    for (int q0 = qb; q0 < qe && res < 0; q0 += CB) {
-        int cand[CB];
+    for (int q = qb; q < qe; q++) {
+        int je = esup[q];
+        if (je == (int)e) continue;
+        int row[SPE];
+        const int4 *rp = reinterpret_cast<const int4 *>(inpoel + (i64)je * SPE);
 #pragma unroll
-        for (int u = 0; u < CB; u++) cand[u] = (q0 + u < qe) ? esup[q0 + u] : -1;
-        int4 rows[CB][SPE / 4];
-#pragma unroll
-        for (int u = 0; u < CB; u++) {
-            const int4 *rp = reinterpret_cast<const int4 *>(inpoel + (i64)(cand[u] < 0 ? 0 : cand[u]) * SPE);
-#pragma unroll
-            for (int v = 0; v < SPE / 4; v++) rows[u][v] = rp[v];
+        for (int v = 0; v < SPE / 4; v++) {
+            int4 x = rp[v];
+            row[4 * v] = x.x; row[4 * v + 1] = x.y; row[4 * v + 2] = x.z; row[4 * v + 3] = x.w;
         }
+        unsigned hit = 0;
 #pragma unroll
-        for (int u = 0; u < CB; u++) {
-            const int je = cand[u];
-            if (je < 0 || je == (int)e || res >= 0) continue;
-            unsigned hit = 0;
-#pragma unroll
-            for (int v = 0; v < SPE / 4; v++) {
-                const int4 x = rows[u][v];
-                const int qn[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    bool h = (qn[k] == mine[0]) | (qn[k] == mine[1]) | (qn[k] == mine[2]) | (qn[k] == mine[3]);
-                    hit |= h ? (1u << (4 * v + k)) : 0u;
-                }
-            }
-            if (__popc(hit) < nj) continue;       // cannot match any face
-            int jt = etype[je];
-            int nf = tab.nfael[jt];
-            bool match = false;
-            for (int l = 0; l < nf; l++) match = match || (__popc(hit & fm.m[jt][l]) == nj);
-            if (match) res = je;
+        for (int k = 0; k < SPE; k++) {
+            int qn = row[k];
+            bool h = (qn == mine[0]) | (qn == mine[1]) | (qn == mine[2]) | (qn == mine[3]);
+            hit |= h ? (1u << k) : 0u;
+        }
+        if (__popc(hit) < nj) continue;       // cannot match any face
+        int jt = etype[je];
+        int nf = tab.nfael[jt];
+        bool match = false;
+        for (int l = 0; l < nf; l++) match = match || (__popc(hit & fm.m[jt][l]) == nj);
+        if (match) {
+            res = je;
+            break;
         }
     }
     esuel[idx] = res;

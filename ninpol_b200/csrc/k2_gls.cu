@@ -1080,12 +1080,12 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
     double tot = warp_sum(part);
     // r_i = 1 - d_i . g_i and sum_i r_i lose digits to cancellation when the system is nearly consistent (residuals
     // << 1, or of mixed sign: one-sided stars, typically 2-D Neumann boundary nodes; in 3-D r_i ~ 1 and the statistic
-    // below sits at 2).  Such nodes go to the dense kernel, which forms r through the reflectors (k2_gls_dense.cu).
+    // below sits at 2.0 - 2.9).  Such nodes go to the dense kernel, which forms r through the reflectors (k2_gls_dense.cu).
     double rmx = 0.0;
     for (int i = lane; i < E; i += 32) rmx = fmax(rmx, fabs(w.front[i]));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rmx = fmax(rmx, __shfl_xor_sync(FULL, rmx, o));
-    if (!(1.0 / rmx + (double)E / fabs(tot) <= 8.0)) return 1;
+    if (!(1.0 / rmx + (double)E / fabs(tot) <= 4.0)) return 1;
     __syncwarp();
     double nv = neu ? w.front[E - 1] / tot : 0.0;   // gls.pyx:470-472 (Q3)
     int cnt = 0;

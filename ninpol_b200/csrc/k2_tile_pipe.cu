@@ -95,7 +95,8 @@ struct PipeSmem {
     unsigned char mode[NB], proc[NB];
 };
 
-static_assert((3 * 64 + 4) % 2 == 0 && (64 + 32) % 16 == 0 && (1408 + 8) % 4 == 0 && (1024 + 8) % 4 == 0 && (128 + 32) % 16 == 0,
+static_assert((3 * 64 + 4) % 2 == 0 && (64 + 32) % 16 == 0 && (32 + 32) % 16 == 0 && (16 + 32) % 16 == 0 && (1408 + 8) % 4 == 0 &&
+                  (768 + 8) % 4 == 0 && (384 + 8) % 4 == 0,
               "ring rows of PipeSmem must be multiples of 16 bytes");
 
 template <int METHOD, int NB, int ECAP, int T, int MINB>
@@ -333,48 +334,59 @@ __global__ void __launch_bounds__(T, MINB) k_tile_pipe(TileArgs a)
     }
 }
 
-// Tile shapes: 64 nodes x 1408 entries on 256 threads for stars of >= 22 elements (tets: 58 nodes per tile at E = 24),
-// 128 nodes x 1024 entries for small stars (8 hexes around a node).  ~100 KB of shared memory: two CTAs per SM.
-#define PIPE_T 256
-template <int METHOD, int NB, int ECAP>
-static int launch_variant(npb_ctx *c, const TileArgs &a, int grid_cap)
+// Tile shapes (nodes x entries, threads, resident CTAs the launch bound asks for).  The prefetch rings cost 60 bytes of
+// shared memory per entry, so big tiles mean few resident warps while the block barriers between the phases want many:
+//   A  64 x 1408, 256 threads, 2 CTAs / SM (~100 KB each)      B  32 x 768, 128 threads, 4 CTAs / SM (~54 KB)
+//   C  16 x 384,  128 threads, 5 CTAs / SM (~28 KB)            D  16 x 384,  64 threads, 8 CTAs / SM
+template <int METHOD, int NB, int ECAP, int T, int MINB>
+static int launch_variant(npb_ctx *c, TileArgs a)
 {
     typedef PipeSmem<NB, ECAP> S;
     const int smem = (int)sizeof(S);
-    auto kern = k_tile_pipe<METHOD, NB, ECAP, PIPE_T, 2>;
+    auto kern = k_tile_pipe<METHOD, NB, ECAP, T, MINB>;
     static bool configured = false;
     if (!configured) {
         NPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
+    a.nb = ECAP / c->mx_epp > NB ? NB : ECAP / c->mx_epp;
+    if (a.nb < 1) return NPB_ERR_ARG;
     const i64 ntiles = (a.p_hi - a.p_lo + a.nb - 1) / a.nb;
-    int grid = (int)(ntiles < (i64)grid_cap ? ntiles : (i64)grid_cap);
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm > MINB) per_sm = MINB;
+    const i64 cap = (i64)c->sm_count * per_sm;
+    int grid = (int)(ntiles < cap ? ntiles : cap);
     if (grid < 1) return NPB_OK;
-    kern<<<grid, PIPE_T, smem, c->stream>>>(a);
+    kern<<<grid, T, smem, c->stream>>>(a);
     return NPB_OK;
 }
 
+template <int METHOD>
+static int launch_shape(npb_ctx *c, const TileArgs &a, char shape)
+{
+    switch (shape) {
+    case 'A': return launch_variant<METHOD, 64, 1408, 256, 2>(c, a);
+    case 'B': return launch_variant<METHOD, 32, 768, 128, 4>(c, a);
+    case 'C': return launch_variant<METHOD, 16, 384, 128, 5>(c, a);
+    case 'D': return launch_variant<METHOD, 16, 384, 64, 8>(c, a);
+    }
+    return NPB_ERR_ARG;
+}
+
 // *used = 1 when the pipelined kernel took the launch, 0 when the caller should use the plain tile kernel.
-// The tile size is chosen here (any tile size gives the same results): 64 nodes x 1408 entries, or 128 x 1024 for
-// small stars.
-int npb_tile_pipe_launch(npb_ctx *c, const TileArgs &a_in, int method, int *used)
+// Selected with NPB_TILE_PIPE=A|B|C|D (measured on B200: see DESIGN.md for which shape, if any, beats the plain
+// kernels); any tile size gives the same results.
+int npb_tile_pipe_launch(npb_ctx *c, const TileArgs &a, int method, int *used)
 {
     *used = 0;
-    const char *off = getenv("NPB_TILE_NO_PIPE");   // A/B timing and tests: the round-1 tile kernels
-    if (off && off[0] == '1') return NPB_OK;
-    if (c->mx_epp < 1) return NPB_OK;
-    TileArgs a = a_in;
-    const int cap = c->sm_count * 2;
-    if (c->mx_epp <= 16) {
-        a.nb = 1024 / c->mx_epp > 128 ? 128 : 1024 / c->mx_epp;
-        if (method == NPB_METHOD_IDW) NPB_TRY((launch_variant<NPB_METHOD_IDW, 128, 1024>(c, a, cap)));
-        else NPB_TRY((launch_variant<NPB_METHOD_LS, 128, 1024>(c, a, cap)));
-    } else if (c->mx_epp <= 1408) {
-        a.nb = 1408 / c->mx_epp > 64 ? 64 : 1408 / c->mx_epp;
-        if (method == NPB_METHOD_IDW) NPB_TRY((launch_variant<NPB_METHOD_IDW, 64, 1408>(c, a, cap)));
-        else NPB_TRY((launch_variant<NPB_METHOD_LS, 64, 1408>(c, a, cap)));
-    } else
-        return NPB_OK;
+    const char *sel = getenv("NPB_TILE_PIPE");
+    if (!sel || !sel[0] || sel[0] == '0') return NPB_OK;
+    char shape = sel[0];
+    if (shape < 'A' || shape > 'D' || c->mx_epp < 1) return NPB_OK;
+    const int ecap = shape == 'A' ? 1408 : shape == 'B' ? 768 : 384;
+    if (c->mx_epp > ecap) return NPB_OK;
+    if (method == NPB_METHOD_IDW) NPB_TRY(launch_shape<NPB_METHOD_IDW>(c, a, shape));
+    else NPB_TRY(launch_shape<NPB_METHOD_LS>(c, a, shape));
     *used = 1;
     return NPB_OK;
 }

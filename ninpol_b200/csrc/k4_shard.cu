@@ -18,6 +18,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -50,6 +51,7 @@ static int load_nccl()
     SYM(CommInitRank, "ncclCommInitRank")
     SYM(CommDestroy, "ncclCommDestroy")
     SYM(Broadcast, "ncclBroadcast")
+    SYM(AllReduce, "ncclAllReduce")
     SYM(Send, "ncclSend")
     SYM(Recv, "ncclRecv")
     SYM(GroupStart, "ncclGroupStart")
@@ -186,36 +188,24 @@ int npb_k4_gather_blocks(npb_ctx *c)
     return NPB_OK;
 }
 
-// Every rank contributes one int; *any = 1 when some rank's is non-zero.  One grouped 1-int broadcast per rank on
-// the compute stream (the same exchange as npb_comm_barrier), then the world ints come back through the mapped block.
+// Every rank contributes one int; *any = 1 when some rank's is non-zero: ONE 4-byte ncclAllReduce (sum) on the
+// compute stream - the only exchange of a planned IDW / LS step - whose result comes back through the mapped block.
 __global__ void k_set_int(int *p, int v) { *p = v; }
-__global__ void k_copy_ints(int *dst, const int *src, int n)
-{
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
-}
 
 int npb_k4_share_flags(npb_ctx *c, int mine, int *any)
 {
     *any = mine;
     if (c->world == 1) return NPB_OK;
-    if (c->world > 16) {
-        npb_set_error("npb_k4_share_flags: world > 16 not supported");
-        return NPB_ERR_ARG;
-    }
     NcclApi *api = c->nccl;
     ncclComm_t comm = (ncclComm_t)c->comm;
-    int *buf = c->counters + 48;
-    k_set_int<<<1, 1, 0, c->stream>>>(buf + c->rank, mine);
+    int *buf = c->counters + 47;
+    k_set_int<<<1, 1, 0, c->stream>>>(buf, mine != 0 ? 1 : 0);
     NPB_LAUNCH(c);
-    NPB_NCCL(api->GroupStart());
-    for (int r = 0; r < c->world; r++) NPB_NCCL(api->Broadcast(buf + r, buf + r, 1, ncclInt32, r, comm, c->stream));
-    NPB_NCCL(api->GroupEnd());
-    k_copy_ints<<<1, 32, 0, c->stream>>>(c->d_small + 16, buf, c->world);
+    NPB_NCCL(api->AllReduce(buf, buf, 1, ncclInt32, ncclSum, comm, c->stream));
+    k_copy_int<<<1, 1, 0, c->stream>>>(c->d_small + 16, buf);
     NPB_LAUNCH(c);
     NPB_CUDA(cudaStreamSynchronize(c->stream));
-    int a = 0;
-    for (int r = 0; r < c->world; r++) a |= (c->h_small[16 + r] != 0);
-    *any = a;
+    *any = c->h_small[16] != 0 ? 1 : 0;
     return NPB_OK;
 }
 

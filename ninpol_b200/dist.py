@@ -51,7 +51,10 @@ def exchange_bytes(payload, rank, world, addr="127.0.0.1", port=29517, timeout=3
             time.sleep(0.05)
     buf = b""
     while len(buf) < 4:
-        buf += s.recv(4 - len(buf))
+        chunk = s.recv(4 - len(buf))
+        if not chunk:
+            raise ConnectionError("unique-id exchange: peer closed before the header arrived")
+        buf += chunk
     n = struct.unpack("<I", buf)[0]
     out = b""
     while len(out) < n:

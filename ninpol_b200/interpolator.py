@@ -141,7 +141,9 @@ class Interpolator:
         self.faces_data_dimensions = np.zeros(1, dtype=DTYPE_I)
         self.logging = logging
         self.logger = _Logger(name, logging)
-        self.CACHE_PATH = tempfile.gettempdir()
+        # the reference caches under tempfile.gettempdir() itself; a world-writable directory lets any user plant a
+        # pickle, so the cache lives in a per-user 0700 directory below it (same file names inside)
+        self.CACHE_PATH = self._private_cache_dir()
         self.mesh_obj = None
         self.grid = None
         self.points_coords = None
@@ -162,6 +164,7 @@ class Interpolator:
         # uploads of the GLS cell fields, the kernels, the NCCL gather and the downloads of the CSR blocks overlap
         # (npb_interpolate_run); results are bit-identical to the plain count + fetch path (stream_chunks=0)
         self.stream_chunks = int(stream_chunks)
+        self.min_chunk_nodes = 200_000     # chunks only pay when each is long next to the launch / copy latencies
         if self.comm.world > 1:
             self._ctx.comm_init(self.comm.unique_id, self.comm.rank, self.comm.world)
             self._ctx.set_gather(gather)
@@ -193,7 +196,30 @@ class Interpolator:
     # ------------------------------------------------------------------------------------------
     # cache helpers (interpolator.pyx:93-111) — inputs-only pickle cache, file meshes only
     # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _private_cache_dir():
+        uid = os.getuid() if hasattr(os, "getuid") else 0
+        path = os.path.join(tempfile.gettempdir(), f"ninpol_b200-{uid}")
+        try:
+            os.makedirs(path, mode=0o700, exist_ok=True)
+            st = os.stat(path)
+            if (hasattr(os, "getuid") and st.st_uid != uid) or (st.st_mode & 0o077):
+                os.chmod(path, 0o700)          # raises when the directory is somebody else's
+                if os.stat(path).st_uid != uid:
+                    raise PermissionError(path)
+        except OSError:
+            path = tempfile.mkdtemp(prefix="ninpol_b200-")   # private by construction
+        return path
+
+    @staticmethod
+    def _source_stamp(filename):
+        st = os.stat(filename)
+        return (int(st.st_size), int(st.st_mtime_ns))
+
     def is_cached(self, filename):
+        """Path of the cache of `filename` (interpolator.pyx:93-102: <basename><hex(size)>.pkl), or None.  The name
+        alone does not identify a mesh (two files of equal name and size): the cache also records the source's size and
+        modification time and is ignored when they differ."""
         if filename == "":
             return None
         little_hash = hex(os.path.getsize(filename))
@@ -208,10 +234,15 @@ class Interpolator:
         if filename == "" and mesh_obj is None:
             raise ValueError("Filename for the mesh or meshio.Mesh object must be provided.")
         cached = self.is_cached(filename)
+        cache = None
         if cached:
-            self.logger.log("Loading mesh from cache")
             with open(cached, "rb") as f:
                 cache = pickle.load(f)
+            if cache.get("source_stamp") != self._source_stamp(filename) or \
+                    cache.get("source_path") != os.path.abspath(filename):
+                cache, cached = None, None       # another file of the same name and size: rebuild
+        if cached:
+            self.logger.log("Loading mesh from cache")
             args = cache["grid"]
             ic = cache["interpolator"]
             self._set_dense("cells", ic["cells_data"])
@@ -278,8 +309,11 @@ class Interpolator:
             little_hash = hex(os.path.getsize(filename))
             pkl_name = filename.split(os.path.sep)[-1].split(".")[0] + little_hash + ".pkl"
             final_path = os.path.join(self.CACHE_PATH, pkl_name)
+            payload = self.make_cache(args)
+            payload["source_stamp"] = self._source_stamp(filename)
+            payload["source_path"] = os.path.abspath(filename)
             with open(final_path, "wb") as f:
-                pickle.dump(self.make_cache(args), f)
+                pickle.dump(payload, f)
             self.logger.log(f"Caching grid to {final_path}")
 
     def make_cache(self, args):
@@ -352,9 +386,26 @@ class Interpolator:
         else:
             self.points_data_dimensions = dims
 
+    def _cell_data_by_type(self):
+        """What `mesh_obj.cell_data_dict` holds (variable -> {cell type -> values}, types in first-appearance order,
+        blocks of one type concatenated in block order), built from `cell_data` / `cells` without copying the array
+        of a type that has a single block - meshio's property concatenates unconditionally, 4 GB at 50M cells."""
+        mesh = self.mesh_obj
+        blocks = getattr(mesh, "cells", None)
+        cd = getattr(mesh, "cell_data", None)
+        if blocks is None or not isinstance(cd, dict) or any(len(v) != len(blocks) for v in cd.values()):
+            return mesh.cell_data_dict
+        out = {}
+        for variable, per_block in cd.items():
+            by_type = {}
+            for values, blk in zip(per_block, blocks):
+                by_type.setdefault(blk.type, []).append(np.asarray(values))
+            out[variable] = {t: (v[0] if len(v) == 1 else np.concatenate(v)) for t, v in by_type.items()}
+        return out
+
     def load_cell_data(self):
         dim = self.grid.dim
-        cell_data_dict = self.mesh_obj.cell_data_dict
+        cell_data_dict = self._cell_data_by_type()
         cell_data = {}
         for variable in cell_data_dict:
             parts = [np.asarray(v) for t, v in cell_data_dict[variable].items() if t in self.types_per_dimension[dim]]
@@ -389,11 +440,29 @@ class Interpolator:
     @staticmethod
     def compute_diffusion_magnitude(permeability):
         """interpolator.pyx:501-509 as the RELEASE build evaluates it: `1 / 3` is C integer division
-        (cdivision=True, setup.py:100-108), so det**0 == 1 and diff_mag = (1 - 3/tr K)^2."""
+        (cdivision=True, setup.py:100-108), so det**0 == 1 and diff_mag = (1 - 3/tr K)^2.
+        Element-wise, so large arrays are cut into slabs for a few threads (numpy releases the GIL): same values."""
         Ks = np.reshape(np.asarray(permeability, dtype=DTYPE_F), (len(permeability), 9))
-        trKs = (Ks[:, 0] + Ks[:, 4]) + Ks[:, 8]          # np.trace order
-        # 3 * det**0 == 3.0 exactly for every det (numpy: x**0 == 1, NaN and inf included)
-        return (1 - (3.0 / trKs)) ** 2
+
+        def slab(a, b):
+            trKs = (Ks[a:b, 0] + Ks[a:b, 4]) + Ks[a:b, 8]          # np.trace order
+            # 3 * det**0 == 3.0 exactly for every det (numpy: x**0 == 1, NaN and inf included)
+            return (1 - (3.0 / trKs)) ** 2
+
+        n = len(Ks)
+        if n < (1 << 21):
+            return slab(0, n)
+        from concurrent.futures import ThreadPoolExecutor
+        workers = max(1, min(8, os.cpu_count() or 1))
+        step = -(-n // (4 * workers))
+        out = np.empty(n, dtype=DTYPE_F)
+
+        def run(a):
+            out[a:a + step] = slab(a, min(n, a + step))
+
+        with ThreadPoolExecutor(max_workers=workers) as ex:
+            list(ex.map(run, range(0, n, step)))
+        return out
 
     def get_dict(self):
         return {"point_ordering": self.point_ordering, "variable_to_index": self.variable_to_index,
@@ -572,11 +641,8 @@ class Interpolator:
             arrays = (self._out("indptr", n_points + 1, np.int32), self._out("indices", cap, np.int32),
                       self._out("data", cap, np.float64), self._out("neumann", n_points, np.float64))
             pinned = self.pinned_outputs
-        # chunks only pay when a chunk is long next to the launch / copy latencies: ~200k nodes each at least
-        lo_hi = (0, n_points) if world == 1 else (int(self.partition_bounds[self.comm.rank]), int(self.partition_bounds[self.comm.rank + 1]))
-        chunks = max(1, min(self.stream_chunks, (lo_hi[1] - lo_hi[0]) // 200_000))
-        if world > 1:                 # every rank must cut the same number of chunks (the NCCL gather is chunked alike)
-            chunks = max(1, min(self.stream_chunks, n_points // (200_000 * world)))
+        # every rank must cut the same number of chunks (the NCCL gather is chunked alike): the rule uses global sizes
+        chunks = max(1, min(self.stream_chunks, n_points // (max(1, self.min_chunk_nodes) * world)))
         if pinned:
             nnz, fell_back = ctx.interpolate_run(method, chunks, perm, dm, *arrays)
         else:                         # pageable outputs: device-resident run, then the staged copies of fetch

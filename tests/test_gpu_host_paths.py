@@ -106,3 +106,35 @@ def test_get_data_get_dict_and_face_data():
     # user row i describes grid face n_f-1-i; data[face_to_grid] (interpolator.pyx:499) undoes the reversal
     got = np.asarray(I.faces_data)[0]
     assert np.array_equal(got, vals[:, 0])
+
+
+def test_cache_is_private_and_not_served_to_another_file_of_equal_name_and_size(tmp_path, fake_meshio):
+    """The reference keys its cache on basename + file size under a world-writable directory; here the cache lives in a
+    per-user 0700 directory and records the source's path, size and mtime, so a different file that merely has the same
+    name and size is rebuilt instead of silently loading the other mesh."""
+    import stat
+    import ninpol_b200
+    from ninpol_b200 import meshgen
+    I = ninpol_b200.Interpolator()
+    st = os.stat(I.CACHE_PATH)
+    assert stat.S_IMODE(st.st_mode) & 0o077 == 0 and st.st_uid == os.getuid()
+    a, b = tmp_path / "a", tmp_path / "b"
+    a.mkdir()
+    b.mkdir()
+    mesh_a = meshgen.make_case("tet", 4)
+    mesh_b = meshgen.make_case("tet", 4, seed=7)            # same sizes, other coordinates and fields
+    pa, pb = str(a / "box.msh"), str(b / "box.msh")
+    for path, mesh in ((pa, mesh_a), (pb, mesh_b)):
+        with open(path, "wb") as f:
+            pickle.dump(mesh, f)
+    assert os.path.getsize(pa) == os.path.getsize(pb)
+    I.CACHE_PATH = str(tmp_path)
+    I.load_mesh(filename=pa)
+    Wa, _ = I.interpolate("u", "idw")
+    J = ninpol_b200.Interpolator()
+    J.CACHE_PATH = str(tmp_path)
+    J.load_mesh(filename=pb)                                 # same cache name: must NOT be served mesh a
+    assert fake_meshio.calls == [pa, pb]
+    Wb, _ = J.interpolate("u", "idw")
+    assert not np.array_equal(Wa.data, Wb.data)
+    assert np.array_equal(np.asarray(J.grid.point_coords), np.asarray(mesh_b.points))

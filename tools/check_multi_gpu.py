@@ -19,6 +19,7 @@ from ninpol_b200 import dist, meshgen
 comm = dist.init_from_env()
 ok = True
 I = ninpol_b200.Interpolator(comm=comm)      # one NCCL communicator per unique id: reuse the object
+I.min_chunk_nodes = 16                       # cut even these small meshes into several chunks per rank
 big = "--big" in sys.argv                    # adds a > 100k-node mesh (Kuhn n = 48: 117,649 nodes)
 
 
