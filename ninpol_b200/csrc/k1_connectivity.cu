@@ -9,6 +9,7 @@
 // All outputs are bit-identical to the reference's (rows ascending, first-encounter face numbering);
 // the equivalences are spelled out in SURVEY.md App. A and checked in tests/test_gpu_parity.py.
 // Everything here is HBM-bound integer work: ids are int32 on the device, rows are compact.
+#include <stdlib.h>
 #include "common.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -213,6 +214,113 @@ k_esuel(ElemTables tab, FaceMasks fm, const int32_t *__restrict__ inpoel, const 
 }
 
 // ------------------------------------------------------------------------------------------------
+// esuel by node stars: one warp per node p matches, inside the star of p held in shared memory, the two sides of
+// every face whose SMALLEST node id is p.  Both elements of such a face contain p, so both are in the star, and every
+// face has exactly one smallest node: each interior face is paired exactly once, with no candidate connectivity
+// fetched from global memory more than once per star (the per-face kernel above reads ~12 candidate rows per face).
+// A side whose face has no equal node set in the star is a boundary face and keeps the -1 esuel was filled with.
+// Equality of node sets is the reference's criterion on conforming meshes (grid.pyx:502-512).
+// ------------------------------------------------------------------------------------------------
+#define STAR_CAPE 64          // elements per star held in shared memory; larger stars set *too_big
+#define STAR_WARPS 4
+template <int SPE>
+__global__ void __launch_bounds__(32 * STAR_WARPS)
+k_esuel_star(ElemTables tab, const int32_t *__restrict__ inpoel, const uint8_t *__restrict__ etype,
+             const int32_t *__restrict__ esup_ptr, const int32_t *__restrict__ esup, i64 n_points, int sfe,
+             int32_t *__restrict__ esuel, int *__restrict__ too_big)
+{
+    __shared__ int s_conn[STAR_WARPS][STAR_CAPE * SPE];
+    __shared__ int s_es[STAR_WARPS][STAR_CAPE];
+    __shared__ unsigned char s_type[STAR_WARPS][STAR_CAPE];
+    __shared__ int s_key[STAR_WARPS][STAR_CAPE * NPB_MX_FE][3];     // the face's other nodes, ascending, -1 padded
+    __shared__ unsigned short s_ij[STAR_WARPS][STAR_CAPE * NPB_MX_FE];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    for (i64 p = (i64)blockIdx.x * STAR_WARPS + wid; p < n_points; p += (i64)gridDim.x * STAR_WARPS) {
+        const int eb = esup_ptr[p], E = esup_ptr[p + 1] - eb;
+        if (E > STAR_CAPE) {
+            if (lane == 0) atomicExch(too_big, 1);
+            continue;
+        }
+        __syncwarp();
+        for (int i = lane; i < E; i += 32) {
+            const int e = esup[eb + i];
+            s_es[wid][i] = e;
+            s_type[wid][i] = etype[e];
+            const int4 *rp = reinterpret_cast<const int4 *>(inpoel + (i64)e * SPE);
+#pragma unroll
+            for (int v = 0; v < SPE / 4; v++) reinterpret_cast<int4 *>(&s_conn[wid][i * SPE])[v] = rp[v];
+        }
+        __syncwarp();
+        // sides (element i, local face j) whose smallest node is p, compacted
+        int P = 0;
+        const int total = E * NPB_MX_FE;
+        for (int idx0 = 0; idx0 < total; idx0 += 32) {
+            const int idx = idx0 + lane;
+            bool ok = false;
+            int k0 = -1, k1 = -1, k2 = -1, i = 0, j = 0;
+            if (idx < total) {
+                i = idx / NPB_MX_FE;
+                j = idx - i * NPB_MX_FE;
+                const int t = s_type[wid][i];
+                if (j < tab.nfael[t]) {
+                    const int nj = tab.lnofa[t][j];
+                    int nd[NPB_MX_PF];
+                    bool has = false;
+                    int mn = 0x7fffffff;
+#pragma unroll
+                    for (int k = 0; k < NPB_MX_PF; k++) {
+                        nd[k] = (k < nj) ? s_conn[wid][i * SPE + tab.lpofa[t][j][k]] : 0x7fffffff;
+                        has = has || nd[k] == (int)p;
+                        mn = min(mn, nd[k]);
+                    }
+                    ok = has && mn == (int)p;
+                    if (ok) {
+                        // the other nodes ascending (p itself sorts first and is dropped; padding sorts last)
+#define NPB_CSWAP(a, b) { int lo_ = min(a, b), hi_ = max(a, b); a = lo_; b = hi_; }
+                        NPB_CSWAP(nd[0], nd[1]) NPB_CSWAP(nd[2], nd[3]) NPB_CSWAP(nd[0], nd[2]) NPB_CSWAP(nd[1], nd[3]) NPB_CSWAP(nd[1], nd[2])
+#undef NPB_CSWAP
+                        k0 = nd[1];
+                        k1 = nd[2];
+                        k2 = nd[3] == 0x7fffffff ? -1 : nd[3];
+                        if (k1 == 0x7fffffff) k1 = -1;
+                    }
+                }
+            }
+            const unsigned bal = __ballot_sync(FULL, ok);
+            if (ok) {
+                const int at = P + __popc(bal & ((1u << lane) - 1u));
+                s_key[wid][at][0] = k0;
+                s_key[wid][at][1] = k1;
+                s_key[wid][at][2] = k2;
+                s_ij[wid][at] = (unsigned short)(i * 8 + j);
+            }
+            P += __popc(bal);
+        }
+        __syncwarp();
+        // pair the sides: side a looks for the first later side b with the same node set and writes both entries
+        for (int a0 = 0; a0 < P; a0 += 32) {
+            const int a = a0 + lane;
+            if (a < P) {
+                const int k0 = s_key[wid][a][0], k1 = s_key[wid][a][1], k2 = s_key[wid][a][2];
+                for (int b = a + 1; b < P; b++) {
+                    if (s_key[wid][b][0] == k0 && s_key[wid][b][1] == k1 && s_key[wid][b][2] == k2) {
+                        const int ija = s_ij[wid][a], ijb = s_ij[wid][b];
+                        const int ea = s_es[wid][ija >> 3], eb2 = s_es[wid][ijb >> 3];
+                        if (ea != eb2) {
+                            esuel[(i64)ea * sfe + (ija & 7)] = eb2;
+                            esuel[(i64)eb2 * sfe + (ijb & 7)] = ea;
+                            break;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Face numbering.  (e, j) owns its face iff it has no neighbour or e < neighbour: that is exactly the
 // face the reference's serial loop numbers when it first meets it (grid.pyx:315-334).
 // ------------------------------------------------------------------------------------------------
@@ -387,7 +495,23 @@ int npb_k1_build(npb_ctx *c, const i64 *h_conn, int cstride, const i64 *h_types,
                 for (int k = 0; k < c->tab.lnofa[t][l]; k++) m |= (unsigned char)(1u << c->tab.lpofa[t][l][k]);
                 fm.m[t][l] = l < c->tab.nfael[t] ? m : 0;
             }
-        if (spe == 4)
+        bool done = false;
+        const char *plain = getenv("NPB_K1_ESUEL_PLAIN");   // A/B timing and tests: the per-face candidate search
+        if (!(plain && plain[0] == '1') && ne * (i64)sfe < (1ll << 31)) {
+            int *too_big = d_mx + 3;
+            NPB_CUDA(cudaMemsetAsync(c->esuel, 0xff, sizeof(int32_t) * ne * sfe, s));   // -1: boundary faces and unused slots
+            const int grid = c->sm_count * 16;
+            if (spe == 4)
+                k_esuel_star<4><<<grid, 32 * STAR_WARPS, 0, s>>>(c->tab, c->inpoel, c->etype, c->esup_ptr, c->esup, np, sfe, c->esuel, too_big);
+            else
+                k_esuel_star<8><<<grid, 32 * STAR_WARPS, 0, s>>>(c->tab, c->inpoel, c->etype, c->esup_ptr, c->esup, np, sfe, c->esuel, too_big);
+            NPB_LAUNCH(c);
+            int h_big = 0;
+            NPB_TRY(npb_read_int(c, too_big, &h_big));
+            done = h_big == 0;      // a star of more than STAR_CAPE elements: the per-face kernel rebuilds everything
+        }
+        if (done) {
+        } else if (spe == 4)
             k_esuel<4><<<npb_blocks(ne * sfe, 256), 256, 0, s>>>(c->tab, fm, c->inpoel, c->etype, c->esup_ptr, c->esup, ne, sfe, c->esuel);
         else
             k_esuel<8><<<npb_blocks(ne * sfe, 256), 256, 0, s>>>(c->tab, fm, c->inpoel, c->etype, c->esup_ptr, c->esup, ne, sfe, c->esuel);

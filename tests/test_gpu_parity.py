@@ -412,3 +412,20 @@ def test_pipelined_tile_kernels_bit_exact(shape, monkeypatch):
                 assert np.array_equal(W.indptr, Wo.indptr) and np.array_equal(W.indices, Wo.indices), (kind, method, chunks)
                 assert np.array_equal(W.data, Wo.data, equal_nan=True), (kind, method, chunks)
                 assert np.array_equal(nv, nvo)
+
+
+@pytest.mark.parametrize("kind,n,kw", [("tet", 9, {"scramble": True}), ("mixed", 10, {"a": 2, "b": 5}), ("quad2d", 9, {"perturb": 0.2})])
+def test_both_esuel_kernels_bit_exact(kind, n, kw, monkeypatch):
+    """esuel comes from the node-star kernel (k_esuel_star) by default and from the per-face candidate search
+    (k_esuel, also the fallback for stars of more than 64 elements) with NPB_K1_ESUEL_PLAIN=1: both equal the oracle."""
+    import ninpol_b200
+    import oracle
+    from ninpol_b200 import meshgen
+    mesh = meshgen.make_case(kind, n, **kw)
+    O = oracle.OracleInterpolator().load_mesh(mesh)
+    for plain in ("0", "1"):
+        monkeypatch.setenv("NPB_K1_ESUEL_PLAIN", plain)
+        I = ninpol_b200.Interpolator()
+        I.load_mesh(mesh_obj=mesh)
+        for name in ("esuel", "infael", "inpofa", "esuf", "esuf_ptr", "boundary_faces", "boundary_points", "fsup"):
+            assert np.array_equal(np.asarray(getattr(I.grid, name)), getattr(O.grid, name)), (name, plain)
