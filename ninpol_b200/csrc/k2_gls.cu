@@ -1163,6 +1163,13 @@ int npb_k2_gls(npb_ctx *c, i64 lo, i64 hi)
             NPB_CUDA(cudaMemcpyToSymbol(c_mf, h_mf, sizeof(h_mf)));
         }
     }
+    // test / A-B switches, read once per pass (the tests flip them between calls of one process)
+    const char *noleaf = getenv("NPB_GLS_NO_LEAF");   // every front through the general loop
+    const int mf_flags = (noleaf && noleaf[0] == '1') ? 1 : 0;
+    const char *cap = getenv("NPB_GLS_CTAS_PER_SM");
+    const int env_cap = cap ? atoi(cap) : 0;
+    const char *var = getenv("NPB_GLS_VARIANT");
+    const int env_variant = var ? atoi(var) : 0;
     float main_ms = 0.f;
     static const char *cls_names[MF_NCLASS] = {"", "k2_gls_c1", "k2_gls_c2", "k2_gls_c3", "k2_gls_c4", "k2_gls_c5", "k2_gls_c6", "k2_gls_c7", "k2_gls_dense"};
     for (int k = 1; k < MF_NCLASS; k++) c->timings.erase(cls_names[k]);
@@ -1178,14 +1185,10 @@ int npb_k2_gls(npb_ctx *c, i64 lo, i64 hi)
         // resident warps per SM are bounded by shared memory; the launch bound follows it so that small
         // stars trade registers for residency (24: 80 registers, 16: 128, 12: 168)
         int per_sm = (int)((227 * 1024) / (smem + 1024));
-        const char *noleaf = getenv("NPB_GLS_NO_LEAF");   // tests / A-B timing: every front through the general loop
-        const int mf_flags = (noleaf && noleaf[0] == '1') ? 1 : 0;
-        const char *cap = getenv("NPB_GLS_CTAS_PER_SM");
-        if (cap && atoi(cap) > 0 && per_sm > atoi(cap)) per_sm = atoi(cap);
+        if (env_cap > 0 && per_sm > env_cap) per_sm = env_cap;
         if (per_sm > 32) per_sm = 32;
         int variant = per_sm >= 16 ? 16 : 12;   // 24 (80 registers) spills the leaf fronts: only on request
-        const char *var = getenv("NPB_GLS_VARIANT");
-        if (var && (atoi(var) == 12 || atoi(var) == 16 || atoi(var) == 24)) variant = atoi(var);
+        if (env_variant == 12 || env_variant == 16 || env_variant == 24) variant = env_variant;
         const int vregs = variant == 24 ? 80 : variant == 16 ? 128 : 168;
         if (per_sm > 65536 / (32 * vregs)) per_sm = 65536 / (32 * vregs);
         int grid = c->sm_count * per_sm;

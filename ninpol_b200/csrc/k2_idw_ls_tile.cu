@@ -38,6 +38,12 @@
 #define LS_NB_WIDE 128
 #endif
 #define IDW_EPS ((double)1.0000000036274937e-15f) /* float32(1e-15), idw.pyx:53 */
+#ifndef IDW_DEFAULT_VARIANT
+#define IDW_DEFAULT_VARIANT 0
+#endif
+#ifndef LS_DEFAULT_VARIANT
+#define LS_DEFAULT_VARIANT 0
+#endif
 
 // rowcnt[p] = entries node p will emit if no weight is an exact zero; neumann[p] = 0
 __global__ void k_row_plan(const int32_t *__restrict__ esup_ptr, const uint8_t *__restrict__ bpoint,
@@ -56,8 +62,9 @@ __global__ void k_row_plan(const int32_t *__restrict__ esup_ptr, const uint8_t *
 }
 
 
-template <int NBCAP>
-__global__ void __launch_bounds__(TILE_T, 7) k_idw_tile(TileArgs a)
+// MLPB = centroid loads batched per thread in phase A (0: the plain per-entry loop); MINB = resident CTAs asked for
+template <int NBCAP, int MINB, int MLPB>
+__global__ void __launch_bounds__(TILE_T, MINB) k_idw_tile(TileArgs a)
 {
     __shared__ double s_r[IDW_ECAP + NBCAP];
     __shared__ int s_e[IDW_ECAP];
@@ -85,25 +92,70 @@ __global__ void __launch_bounds__(TILE_T, 7) k_idw_tile(TileArgs a)
         if (tid < nb)
             for (int k = s_ptr[tid] - eb; k < s_ptr[tid + 1] - eb; k++) s_rid[k] = (unsigned char)tid;
         __syncthreads();
-        // phase A: one thread per esup entry
-        for (int i = tid; i < ne; i += TILE_T) {
-            int node = s_rid[i];
-            if (!s_proc[node]) continue;
-            int e = a.esup[eb + i];
-            s_e[i] = e;
-            const double *cc = a.cent + (i64)e * 3;
-            double d0 = __dsub_rn(s_x[3 * node], cc[0]);
-            double dist = __dadd_rn(0.0, __dmul_rn(d0, d0));
-            if (a.dim > 1) {
-                double d1 = __dsub_rn(s_x[3 * node + 1], cc[1]);
-                dist = __dadd_rn(dist, __dmul_rn(d1, d1));
+        // phase A: one thread per esup entry.  Memory-level parallelism first: the ids of all of this thread's
+        // entries are fetched with independent loads, then the centroids in batches of MLP_B entries (9 loads in
+        // flight per thread), so a tile costs ~3 dependent global round trips instead of 2 per entry
+        if constexpr (MLPB == 0) {
+            for (int i = tid; i < ne; i += TILE_T) {
+                int node = s_rid[i];
+                if (!s_proc[node]) continue;
+                int e = a.esup[eb + i];
+                s_e[i] = e;
+                const double *cc = a.cent + (i64)e * 3;
+                double d0 = __dsub_rn(s_x[3 * node], cc[0]);
+                double dist = __dadd_rn(0.0, __dmul_rn(d0, d0));
+                if (a.dim > 1) {
+                    double d1 = __dsub_rn(s_x[3 * node + 1], cc[1]);
+                    dist = __dadd_rn(dist, __dmul_rn(d1, d1));
+                }
+                if (a.dim > 2) {
+                    double d2 = __dsub_rn(s_x[3 * node + 2], cc[2]);
+                    dist = __dadd_rn(dist, __dmul_rn(d2, d2));
+                }
+                s_r[i + node] = (dist <= IDW_EPS) ? -1.0 : __ddiv_rn(1.0, __dsqrt_rn(dist));
             }
-            if (a.dim > 2) {
-                double d2 = __dsub_rn(s_x[3 * node + 2], cc[2]);
-                dist = __dadd_rn(dist, __dmul_rn(d2, d2));
+        } else {
+            constexpr int KMAX = (IDW_ECAP + TILE_T - 1) / TILE_T;
+            constexpr int MLP_B = MLPB == 0 ? 1 : MLPB;
+            int ee[KMAX];
+#pragma unroll
+            for (int u = 0; u < KMAX; u++) {
+                const int i = tid + u * TILE_T;
+                ee[u] = (i < ne) ? a.esup[eb + i] : -1;
             }
-            // coincident centroid (idw.pyx:69): marked with -1 (a reciprocal distance is never negative)
-            s_r[i + node] = (dist <= IDW_EPS) ? -1.0 : __ddiv_rn(1.0, __dsqrt_rn(dist));
+#pragma unroll
+            for (int u0 = 0; u0 < KMAX; u0 += MLP_B) {
+                double c[MLP_B][3];
+#pragma unroll
+                for (int v = 0; v < MLP_B; v++) {
+                    const int u = u0 + v;
+                    if (u < KMAX && ee[u >= KMAX ? 0 : u] >= 0) {
+                        const double *cc = a.cent + (i64)ee[u >= KMAX ? 0 : u] * 3;
+                        c[v][0] = cc[0]; c[v][1] = cc[1]; c[v][2] = cc[2];
+                    }
+                }
+#pragma unroll
+                for (int v = 0; v < MLP_B; v++) {
+                    const int u = u0 + v;
+                    if (u >= KMAX || ee[u >= KMAX ? 0 : u] < 0) continue;
+                    const int i = tid + u * TILE_T;
+                    const int node = s_rid[i];
+                    s_e[i] = ee[u >= KMAX ? 0 : u];
+                    if (!s_proc[node]) continue;
+                    double d0 = __dsub_rn(s_x[3 * node], c[v][0]);
+                    double dist = __dadd_rn(0.0, __dmul_rn(d0, d0));
+                    if (a.dim > 1) {
+                        double d1 = __dsub_rn(s_x[3 * node + 1], c[v][1]);
+                        dist = __dadd_rn(dist, __dmul_rn(d1, d1));
+                    }
+                    if (a.dim > 2) {
+                        double d2 = __dsub_rn(s_x[3 * node + 2], c[v][2]);
+                        dist = __dadd_rn(dist, __dmul_rn(d2, d2));
+                    }
+                    // coincident centroid (idw.pyx:69): marked with -1 (a reciprocal distance is never negative)
+                    s_r[i + node] = (dist <= IDW_EPS) ? -1.0 : __ddiv_rn(1.0, __dsqrt_rn(dist));
+                }
+            }
         }
         __syncthreads();
         // phase B: one thread per node, sequential sum in esup order (idw.pyx:79)
@@ -162,8 +214,8 @@ __global__ void __launch_bounds__(TILE_T, 7) k_idw_tile(TileArgs a)
 // NBCAP = node capacity of a tile: 64 for stars of >= 22 elements (tets); 128 (with 1024 entries) for small
 // stars such as the 8 hexes around a node, where 64 nodes would use a third of the entry capacity and leave
 // 3/4 of the threads idle in phase B (hex 200^3: 1.53 -> 1.08 ms)
-template <int ECAP, int NBCAP>
-__global__ void __launch_bounds__(TILE_T, LS_MINB) k_ls_tile(TileArgs a)
+template <int ECAP, int NBCAP, int MINB, int MLPB>
+__global__ void __launch_bounds__(TILE_T, MINB) k_ls_tile(TileArgs a)
 {
     __shared__ double s_vx[ECAP + NBCAP], s_vy[ECAP + NBCAP], s_vz[ECAP + NBCAP];
     __shared__ int s_e[ECAP];
@@ -191,16 +243,51 @@ __global__ void __launch_bounds__(TILE_T, LS_MINB) k_ls_tile(TileArgs a)
         if (tid < nb)
             for (int k = s_ptr[tid] - eb; k < s_ptr[tid + 1] - eb; k++) s_rid[k] = (unsigned char)tid;
         __syncthreads();
-        // phase A: v = centroid - x_v per entry (ls.pyx:65-67)
-        for (int i = tid; i < ne; i += TILE_T) {
-            int node = s_rid[i];
-            if (!s_proc[node]) continue;
-            int e = a.esup[eb + i];
-            s_e[i] = e;
-            const double *cc = a.cent + (i64)e * 3;
-            s_vx[i + node] = S2(cc[0], s_x[3 * node]);
-            s_vy[i + node] = S2(cc[1], s_x[3 * node + 1]);
-            s_vz[i + node] = S2(cc[2], s_x[3 * node + 2]);
+        // phase A: v = centroid - x_v per entry (ls.pyx:65-67); ids first, then the centroids in batches (see k_idw_tile)
+        if constexpr (MLPB == 0) {
+            for (int i = tid; i < ne; i += TILE_T) {
+                int node = s_rid[i];
+                if (!s_proc[node]) continue;
+                int e = a.esup[eb + i];
+                s_e[i] = e;
+                const double *cc = a.cent + (i64)e * 3;
+                s_vx[i + node] = S2(cc[0], s_x[3 * node]);
+                s_vy[i + node] = S2(cc[1], s_x[3 * node + 1]);
+                s_vz[i + node] = S2(cc[2], s_x[3 * node + 2]);
+            }
+        } else {
+            constexpr int KMAX = (ECAP + TILE_T - 1) / TILE_T;
+            constexpr int MLP_B = MLPB == 0 ? 1 : MLPB;
+            int ee[KMAX];
+#pragma unroll
+            for (int u = 0; u < KMAX; u++) {
+                const int i = tid + u * TILE_T;
+                ee[u] = (i < ne) ? a.esup[eb + i] : -1;
+            }
+#pragma unroll
+            for (int u0 = 0; u0 < KMAX; u0 += MLP_B) {
+                double c[MLP_B][3];
+#pragma unroll
+                for (int v = 0; v < MLP_B; v++) {
+                    const int u = u0 + v;
+                    if (u < KMAX && ee[u >= KMAX ? 0 : u] >= 0) {
+                        const double *cc = a.cent + (i64)ee[u >= KMAX ? 0 : u] * 3;
+                        c[v][0] = cc[0]; c[v][1] = cc[1]; c[v][2] = cc[2];
+                    }
+                }
+#pragma unroll
+                for (int v = 0; v < MLP_B; v++) {
+                    const int u = u0 + v;
+                    if (u >= KMAX || ee[u >= KMAX ? 0 : u] < 0) continue;
+                    const int i = tid + u * TILE_T;
+                    const int node = s_rid[i];
+                    s_e[i] = ee[u >= KMAX ? 0 : u];
+                    if (!s_proc[node]) continue;
+                    s_vx[i + node] = S2(c[v][0], s_x[3 * node]);
+                    s_vy[i + node] = S2(c[v][1], s_x[3 * node + 1]);
+                    s_vz[i + node] = S2(c[v][2], s_x[3 * node + 2]);
+                }
+            }
         }
         __syncthreads();
         // phase B: per node, the nine moments summed in esup order, then Cramer's rule (ls.pyx:69-126)
@@ -313,14 +400,34 @@ static int tile_launch(npb_ctx *c, const TileArgs &a, int method)
     NpbTimer tm(c, "k2_main");
     int piped = 0;
     NPB_TRY(npb_tile_pipe_launch(c, a, method, &piped));
+    // NPB_TILE_VARIANT=<digit for IDW><digit for LS> picks among the compiled (resident CTAs, load batch) variants for
+    // A/B timing; the defaults are the measured best
+    const char *tv = getenv("NPB_TILE_VARIANT");
+    const int vi = (tv && tv[0] >= '0' && tv[0] <= '9') ? tv[0] - '0' : IDW_DEFAULT_VARIANT;
+    const int vl = (tv && tv[0] && tv[1] >= '0' && tv[1] <= '9') ? tv[1] - '0' : LS_DEFAULT_VARIANT;
     if (piped) {
     } else if (method == NPB_METHOD_IDW) {
-        k_idw_tile<TILE_NB><<<grid, TILE_T, 0, c->stream>>>(a);
+        switch (vi) {
+        case 1: k_idw_tile<TILE_NB, 7, 2><<<grid, TILE_T, 0, c->stream>>>(a); break;
+        case 2: k_idw_tile<TILE_NB, 6, 2><<<grid, TILE_T, 0, c->stream>>>(a); break;
+        case 3: k_idw_tile<TILE_NB, 5, 3><<<grid, TILE_T, 0, c->stream>>>(a); break;
+        case 4: k_idw_tile<TILE_NB, 4, 6><<<grid, TILE_T, 0, c->stream>>>(a); break;
+        default: k_idw_tile<TILE_NB, 7, 0><<<grid, TILE_T, 0, c->stream>>>(a); break;
+        }
+    } else if (a.nb > TILE_NB) {
+        switch (vl) {
+        case 1: k_ls_tile<LS_ECAP_WIDE, LS_NB_WIDE, 4, 2><<<grid, TILE_T, 0, c->stream>>>(a); break;
+        case 2: k_ls_tile<LS_ECAP_WIDE, LS_NB_WIDE, 4, 4><<<grid, TILE_T, 0, c->stream>>>(a); break;
+        case 3: k_ls_tile<LS_ECAP_WIDE, LS_NB_WIDE, 3, 4><<<grid, TILE_T, 0, c->stream>>>(a); break;
+        default: k_ls_tile<LS_ECAP_WIDE, LS_NB_WIDE, 4, 0><<<grid, TILE_T, 0, c->stream>>>(a); break;
+        }
     } else {
-        if (a.nb > TILE_NB)
-            k_ls_tile<LS_ECAP_WIDE, LS_NB_WIDE><<<grid, TILE_T, 0, c->stream>>>(a);
-        else
-            k_ls_tile<LS_ECAP, TILE_NB><<<grid, TILE_T, 0, c->stream>>>(a);
+        switch (vl) {
+        case 1: k_ls_tile<LS_ECAP, TILE_NB, 4, 2><<<grid, TILE_T, 0, c->stream>>>(a); break;
+        case 2: k_ls_tile<LS_ECAP, TILE_NB, 4, 3><<<grid, TILE_T, 0, c->stream>>>(a); break;
+        case 3: k_ls_tile<LS_ECAP, TILE_NB, 3, 6><<<grid, TILE_T, 0, c->stream>>>(a); break;
+        default: k_ls_tile<LS_ECAP, TILE_NB, 4, 0><<<grid, TILE_T, 0, c->stream>>>(a); break;
+        }
     }
     NPB_LAUNCH(c);
     NPB_CUDA(cudaGetLastError());

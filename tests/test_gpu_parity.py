@@ -429,3 +429,22 @@ def test_both_esuel_kernels_bit_exact(kind, n, kw, monkeypatch):
         I.load_mesh(mesh_obj=mesh)
         for name in ("esuel", "infael", "inpofa", "esuf", "esuf_ptr", "boundary_faces", "boundary_points", "fsup"):
             assert np.array_equal(np.asarray(getattr(I.grid, name)), getattr(O.grid, name)), (name, plain)
+
+
+@pytest.mark.parametrize("variant", ["11", "22", "33", "40"])
+def test_tile_kernel_variants_bit_exact(variant, monkeypatch):
+    """The load-batched variants of the plain IDW / LS tile kernels (NPB_TILE_VARIANT) are the same arithmetic."""
+    import ninpol_b200
+    import oracle
+    from ninpol_b200 import meshgen
+    monkeypatch.setenv("NPB_TILE_VARIANT", variant)
+    for kind, n, kw in (("tet", 14, {}), ("hex", 20, {}), ("mixed", 12, {"a": 3, "b": 6}), ("quad2d", 9, {"perturb": 0.2})):
+        mesh = meshgen.make_case(kind, n, **kw)
+        O = oracle.OracleInterpolator().load_mesh(mesh)
+        I = ninpol_b200.Interpolator()
+        I.load_mesh(mesh_obj=mesh)
+        for method in ("idw", "ls"):
+            W, nv = I.interpolate("u", method)
+            Wo, nvo = O.interpolate("u", method)
+            assert np.array_equal(W.indptr, Wo.indptr) and np.array_equal(W.indices, Wo.indices), (kind, method)
+            assert np.array_equal(W.data, Wo.data, equal_nan=True), (kind, method)
