@@ -416,13 +416,18 @@ def run_ours(args, rank, world):
     I_kwargs = {"gather": e2e_gather, "stream_chunks": args.stream_chunks}
     t0 = time.time()
     I = ninpol_b200.Interpolator(comm=comm, **I_kwargs)
+    t_ctor = time.time() - t0
+    t0 = time.time()
     I.load_mesh(mesh_obj=mesh)
     t_load = time.time() - t0
     ctx = I._ctx
     g = I.grid
     n_points, n_elems = g.n_points, g.n_elems
+    host_phases = {k: round(I.last_timings.get(k, 0.0), 3) for k in ("load_mesh_process_s", "load_mesh_device_call_s", "load_mesh_data_s")}
+    host_phases["constructor_s"] = round(t_ctor, 3)
     k1 = {k: ctx.timing_or(k) for k in ("k1", "k1_esup", "k1_esuel", "k1_faces", "k1_fsup", "k1_geom", "h2d_mesh")}
     if rank == 0:
+        log(f"Interpolator() {t_ctor:.2f}s (CUDA context, NCCL communicator); load_mesh phases {host_phases}")
         log(f"load_mesh {t_load:.2f}s wall; device K1 {k1['k1']:.1f} ms (esup {k1['k1_esup']:.1f}, esuel {k1['k1_esuel']:.1f}, "
             f"faces {k1['k1_faces']:.1f}, fsup {k1['k1_fsup']:.1f}, geom {k1['k1_geom']:.1f}); H2D {k1['h2d_mesh']:.1f} ms")
     method = args.method
@@ -484,7 +489,7 @@ def run_ours(args, rank, world):
         "step_ms_median": dev["step_ms_median"], "step_ms_best": dev["step_ms_best"],
         "e2e": e2e, "gpu_launches": dev["launches"], "clocks": dev["clocks"], "roofline": roof,
         "load_mesh": {"k1_device_ms": k1["k1"], "h2d_ms": k1["h2d_mesh"], "cells_per_s_device": n_elems / (k1["k1"] * 1e-3) if k1["k1"] else None,
-                      "wall_s": plumb.max(t_load), "breakdown_ms": k1,
+                      "wall_s": plumb.max(t_load), "host_phases_s": host_phases, "breakdown_ms": k1,
                       "k1_roofline": {"bound": "hbm", "algorithmic_bytes": 292.0 * n_elems if kind == "tet" else None,
                                       "frac": (292.0 * n_elems / (k1["k1"] * 1e-3) / 1e9 / roof["peak"]) if (kind == "tet" and k1["k1"]) else None}},
     }

@@ -233,6 +233,7 @@ class Interpolator:
     def load_mesh(self, filename="", mesh_obj=None):
         if filename == "" and mesh_obj is None:
             raise ValueError("Filename for the mesh or meshio.Mesh object must be provided.")
+        t_begin = time.time()
         cached = self.is_cached(filename)
         cache = None
         if cached:
@@ -274,8 +275,10 @@ class Interpolator:
             c3[:, :coords.shape[1]] = coords
             coords = c3
         t0 = time.time()
+        self.last_timings["load_mesh_process_s"] = t0 - t_begin
         self._ctx.load_mesh(dim, n_elems, n_points, connectivity, element_types, npoel, nfael, lnofa, lpofa, nedel,
                             lpoed, coords, self.build_edges)
+        self.last_timings["load_mesh_device_call_s"] = time.time() - t0
         self.grid = Grid(self._ctx, (npoel, nfael, lnofa, lpofa, nedel, lpoed), self.logging, self.build_edges)
         self.logger.log(f"Grid built in {time.time() - t0:.2f} seconds")
         self.last_timings["load_mesh_device_ms"] = self._ctx.timing_or("k1")
@@ -294,6 +297,7 @@ class Interpolator:
                 self._set_dense("points", np.zeros((1, 1), dtype=DTYPE_F))
                 self.points_data_dimensions = np.zeros(1, dtype=DTYPE_I)
             self.logger.log(f"Data loaded in {time.time() - t0:.2f} seconds")
+            self.last_timings["load_mesh_data_s"] = time.time() - t0
         self.is_grid_initialized = True
         for reg in self._registered.values():
             reg.release()

@@ -15,3 +15,5 @@ print("k4", d.get("k4")); print("load_mesh wall", d["load_mesh"]["wall_s"])
 for m,v in d.get("also",{}).items(): print("also", m, "%.4g"%v["value"], "ms %.3f kernel %.3f by-step frac %.3f"%(v["ms_per_step"], v["kernel_ms"], v["roofline_by_step_time"]["frac"]), v.get("with_nccl_gather"))
 for k,v in d.get("configs",{}).items(): print(k, {m:(round(x["value"]), round(x["e2e"]["value"])) for m,x in v.get("methods",{}).items()}, v.get("error"))
 PY
+python -m pytest tests/test_gpu_parity.py -q -m gpu -k "2d_gls or variants or esuel or pipelined" 2>&1 | tail -4
+python tools/tile_sweep.py tet203 hex200 > gpurun_out/r02_tile_sweep2.log 2>&1; echo "sweep rc=$?"; cat gpurun_out/r02_tile_sweep2.log | tail -40
