@@ -365,14 +365,12 @@ def roofline_block(I, method, kernel_ms, lo, hi, share_of, workload):
     return out, flops, prof
 
 
-def run_config(I_kwargs, comm, plumb, key, workload, methods, neumann_rate, steps):
-    """A short run of another BASELINE config on the same GPUs: device-timed value + roofline per method, e2e for
-    the first method."""
-    import ninpol_b200
+def run_config(I, I_kwargs, comm, plumb, key, workload, methods, neumann_rate, steps):
+    """A short run of another BASELINE config on the same GPUs (same Interpolator: one NCCL communicator per unique id):
+    device-timed value + roofline + e2e per method."""
     kind, n, desc = WORKLOADS[workload]
     mesh = make_mesh(kind, n, neumann_rate)
     t0 = time.time()
-    I = ninpol_b200.Interpolator(comm=comm, **I_kwargs)
     I.load_mesh(mesh_obj=mesh)
     t_load = time.time() - t0
     ctx, g = I._ctx, I.grid
@@ -395,7 +393,6 @@ def run_config(I_kwargs, comm, plumb, key, workload, methods, neumann_rate, step
         m["e2e"] = {"value": g.n_points / e2e_s, "unit": "nodes/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h}
         out["methods"][method] = m
-    del I
     return out
 
 
@@ -534,13 +531,12 @@ def run_ours(args, rank, world):
     I.set_gather(e2e_gather)
     # ---- the other BASELINE configs, short runs on the same GPUs ----
     if not args.no_configs:
-        del I
         cfg = {}
         for key, wl, methods, rate in CONFIG_RUNS:
             if args.configs and key not in args.configs.split(","):
                 continue
             try:
-                cfg[key] = run_config(I_kwargs, comm, plumb, key, wl, methods, rate, args.config_steps)
+                cfg[key] = run_config(I, I_kwargs, comm, plumb, key, wl, methods, rate, args.config_steps)
             except Exception as e:   # a side run must never take the headline down
                 cfg[key] = {"error": repr(e)}
             if rank == 0:

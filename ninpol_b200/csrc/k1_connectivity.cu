@@ -222,6 +222,7 @@ k_esuel(ElemTables tab, FaceMasks fm, const int32_t *__restrict__ inpoel, const 
 // Equality of node sets is the reference's criterion on conforming meshes (grid.pyx:502-512).
 // ------------------------------------------------------------------------------------------------
 #define STAR_CAPE 64          // elements per star held in shared memory; larger stars set *too_big
+#define STAR_PAIRS 128        // sides of faces whose smallest node is the star's node (2 per interior face)
 #define STAR_WARPS 4
 template <int SPE>
 __global__ void __launch_bounds__(32 * STAR_WARPS)
@@ -232,8 +233,8 @@ k_esuel_star(ElemTables tab, const int32_t *__restrict__ inpoel, const uint8_t *
     __shared__ int s_conn[STAR_WARPS][STAR_CAPE * SPE];
     __shared__ int s_es[STAR_WARPS][STAR_CAPE];
     __shared__ unsigned char s_type[STAR_WARPS][STAR_CAPE];
-    __shared__ int s_key[STAR_WARPS][STAR_CAPE * NPB_MX_FE][3];     // the face's other nodes, ascending, -1 padded
-    __shared__ unsigned short s_ij[STAR_WARPS][STAR_CAPE * NPB_MX_FE];
+    __shared__ int s_key[STAR_WARPS][STAR_PAIRS][3];     // the face's other nodes, ascending, -1 padded
+    __shared__ unsigned short s_ij[STAR_WARPS][STAR_PAIRS];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
     for (i64 p = (i64)blockIdx.x * STAR_WARPS + wid; p < n_points; p += (i64)gridDim.x * STAR_WARPS) {
@@ -288,6 +289,11 @@ k_esuel_star(ElemTables tab, const int32_t *__restrict__ inpoel, const uint8_t *
                 }
             }
             const unsigned bal = __ballot_sync(FULL, ok);
+            if (P + __popc(bal) > STAR_PAIRS) {      // warp-uniform: more sides than the table holds
+                if (lane == 0) atomicExch(too_big, 1);
+                P = 0;
+                break;
+            }
             if (ok) {
                 const int at = P + __popc(bal & ((1u << lane) - 1u));
                 s_key[wid][at][0] = k0;

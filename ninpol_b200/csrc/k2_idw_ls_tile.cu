@@ -42,7 +42,7 @@
 #define IDW_DEFAULT_VARIANT 0
 #endif
 #ifndef LS_DEFAULT_VARIANT
-#define LS_DEFAULT_VARIANT 0
+#define LS_DEFAULT_VARIANT 1   // measured on B200 (tools/tile_sweep.py): LS 0.39 -> 0.52 (50M tets), 0.42 -> 0.50 (hex 200^3)
 #endif
 
 // rowcnt[p] = entries node p will emit if no weight is an exact zero; neumann[p] = 0
