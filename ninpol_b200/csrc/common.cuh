@@ -16,6 +16,10 @@ typedef long long i64;
 #define NPB_MX_PF 4
 #define NPB_N_TYPES 8
 #define NPB_MX_EE 12
+// Centroids live on the device as [n_elems, 4] doubles (x, y, z, 0): a 32-byte record never straddles two 32-byte
+// sectors, whereas a 24-byte one does half the time - the per-entry centroid gather is the dominant stream of the
+// IDW / LS kernels and goes from 1.5 to 1 sector per entry.  The export strips the pad.
+#define NPB_CSTRIDE 4
 
 // element tables (reference utils/point_ordering.yaml via process_mesh, interpolator.pyx:274-330);
 // passed to kernels by value -> lives in the constant bank.

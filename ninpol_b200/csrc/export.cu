@@ -283,6 +283,14 @@ static int export_rows(npb_ctx *c, const int32_t *src, i64 rows, int ss, int ds,
     return rc;
 }
 
+__global__ void k_strip_pad(const double *__restrict__ in, i64 n, double *__restrict__ out)
+{
+    i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * 3) return;
+    i64 e = idx / 3;
+    out[idx] = in[e * NPB_CSTRIDE + (idx - e * 3)];
+}
+
 static int export_f64(npb_ctx *c, const double *src, i64 n, void *out, i64 cap)
 {
     if (cap < (i64)sizeof(double) * n) {
@@ -298,7 +306,15 @@ int npb_export_array(npb_ctx *c, const char *name, void *out, i64 cap)
 {
     i64 ne = c->n_elems, np = c->n_points, nf = c->n_faces;
     if (!strcmp(name, "point_coords")) return export_f64(c, c->coords, np * 3, out, cap);
-    if (!strcmp(name, "centroids")) return export_f64(c, c->centroids, ne * 3, out, cap);
+    if (!strcmp(name, "centroids")) {   // device records are [n_elems, NPB_CSTRIDE]: strip the pad
+        NpbTmp packed;
+        NPB_CUDA(packed.alloc(sizeof(double) * (size_t)ne * 3));
+        if (ne > 0) {
+            k_strip_pad<<<npb_blocks(ne * 3, 256), 256, 0, c->stream>>>(c->centroids, ne, packed.as<double>());
+            NPB_LAUNCH(c);
+        }
+        return export_f64(c, packed.as<double>(), ne * 3, out, cap);
+    }
     if (!strcmp(name, "faces_centers")) return export_f64(c, c->fcent, nf * 3, out, cap);
     if (!strcmp(name, "normal_faces")) return export_f64(c, c->fnormal, nf * 3, out, cap);
     if (!strcmp(name, "faces_areas")) return export_f64(c, c->farea, nf, out, cap);

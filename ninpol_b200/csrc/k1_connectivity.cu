@@ -541,7 +541,7 @@ int npb_k1_build(npb_ctx *c, const i64 *h_conn, int cstride, const i64 *h_types,
         NPB_TRY(npb_alloc(c, (void **)&c->inpofa, sizeof(int32_t) * nf1 * NPB_MX_PF));
         NPB_TRY(npb_alloc(c, (void **)&c->esuf2, sizeof(int2) * nf1));
         NPB_TRY(npb_alloc(c, (void **)&c->bface, nf1));
-        NPB_TRY(npb_alloc(c, (void **)&c->centroids, sizeof(double) * ne * 3));
+        NPB_TRY(npb_alloc(c, (void **)&c->centroids, sizeof(double) * ne * NPB_CSTRIDE));
         NPB_TRY(npb_alloc(c, (void **)&c->fcent, sizeof(double) * nf1 * 3));
         NPB_TRY(npb_alloc(c, (void **)&c->fnormal, sizeof(double) * nf1 * 3));
         NPB_TRY(npb_alloc(c, (void **)&c->farea, sizeof(double) * nf1));

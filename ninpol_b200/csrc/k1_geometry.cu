@@ -24,9 +24,8 @@ __global__ void k_centroids(ElemTables tab, const int32_t *__restrict__ inpoel, 
         if (dim > 1) cy = __dadd_rn(cy, __ddiv_rn(x[1], dn));
         if (dim > 2) cz = __dadd_rn(cz, __ddiv_rn(x[2], dn));
     }
-    cent[e * 3 + 0] = cx;
-    cent[e * 3 + 1] = cy;
-    cent[e * 3 + 2] = cz;
+    reinterpret_cast<double2 *>(cent + e * NPB_CSTRIDE)[0] = make_double2(cx, cy);
+    reinterpret_cast<double2 *>(cent + e * NPB_CSTRIDE)[1] = make_double2(cz, 0.0);
 }
 
 __device__ __forceinline__ float cross_norm_sq(float v1x, float v1y, float v1z, float v2x, float v2y, float v2z,

@@ -304,7 +304,7 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
     const bool orig_in_smem = orig_len <= kc.fcap;
     double *orig = orig_in_smem ? w.front : w.arena;
     for (int i = lane; i < E; i += 32) {
-        const double *cc = a.cent + (i64)w.es[i] * 3;
+        const double *cc = a.cent + (i64)w.es[i] * NPB_CSTRIDE;
         double d0 = cc[0] - xv0, d1 = cc[1] - xv1, d2 = cc[2] - xv2;
         w.dvec[3 * i] = d0; w.dvec[3 * i + 1] = d1; w.dvec[3 * i + 2] = d2;
         double *row = orig + 4 * i;                       // [ d^T | 1 ]   gls.pyx:268-281

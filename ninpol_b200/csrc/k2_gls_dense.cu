@@ -43,7 +43,7 @@ __device__ void gls_node_dense(const GlsArgs &a, int p, double *ws)
 
     // element rows (gls.pyx:268-281): [ (x_K - x_v)^T at block i | 1 ]
     for (int i = lane; i < E; i += 32) {
-        const double *cc = a.cent + (i64)es[i] * 3;
+        const double *cc = a.cent + (i64)es[i] * NPB_CSTRIDE;
         double *row = M + (size_t)i * ld;
         row[3 * i + 0] = cc[0] - xv0;
         row[3 * i + 1] = cc[1] - xv1;

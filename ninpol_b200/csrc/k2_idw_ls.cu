@@ -35,7 +35,7 @@ k_idw(const int32_t *__restrict__ esup_ptr, const int32_t *__restrict__ esup, co
     int n_source = 0;
     int zero_at = -1;
     for (int q = b; q < e; q++) {
-        const double *cc = cent + (i64)esup[q] * 3;
+        const double *cc = cent + (i64)esup[q] * NPB_CSTRIDE;
         double d0 = __dsub_rn(x0, cc[0]);
         double dist = __dadd_rn(0.0, __dmul_rn(d0, d0));
         if (dim > 1) {
@@ -87,7 +87,7 @@ k_ls(const int32_t *__restrict__ esup_ptr, const int32_t *__restrict__ esup, con
     double x0 = coords[p * 3 + 0], x1 = coords[p * 3 + 1], x2 = coords[p * 3 + 2];
     double Ix = 0.0, Iy = 0.0, Iz = 0.0, Ixx = 0.0, Ixy = 0.0, Ixz = 0.0, Iyy = 0.0, Iyz = 0.0, Izz = 0.0;
     for (int q = b; q < e; q++) {  // ls.pyx:64-77
-        const double *cc = cent + (i64)esup[q] * 3;
+        const double *cc = cent + (i64)esup[q] * NPB_CSTRIDE;
         double vx = __dsub_rn(cc[0], x0), vy = __dsub_rn(cc[1], x1), vz = __dsub_rn(cc[2], x2);
         Ix = __dadd_rn(Ix, vx);
         Iy = __dadd_rn(Iy, vy);
@@ -110,7 +110,7 @@ k_ls(const int32_t *__restrict__ esup_ptr, const int32_t *__restrict__ esup, con
     if (D == 0.0) {  // inverse-distance fallback, ls.pyx:88-102
         double total = 0.0;
         for (int q = b; q < e; q++) {
-            const double *cc = cent + (i64)esup[q] * 3;
+            const double *cc = cent + (i64)esup[q] * NPB_CSTRIDE;
             double vx = S2(cc[0], x0), vy = S2(cc[1], x1), vz = S2(cc[2], x2);
             double r = __ddiv_rn(1.0, __dsqrt_rn(A2(A2(M2(vx, vx), M2(vy, vy)), M2(vz, vz))));
             w[q - b] = r;
@@ -135,7 +135,7 @@ k_ls(const int32_t *__restrict__ esup_ptr, const int32_t *__restrict__ esup, con
                              M2(Iz, S2(M2(Ixy, Ixy), M2(Ixx, Iyy)))), D);
     double denom = A2(A2(A2((double)(e - b), M2(lx, Ix)), M2(ly, Iy)), M2(lz, Iz));  // ls.pyx:126
     for (int q = b; q < e; q++) {
-        const double *cc = cent + (i64)esup[q] * 3;
+        const double *cc = cent + (i64)esup[q] * NPB_CSTRIDE;
         double vx = S2(cc[0], x0), vy = S2(cc[1], x1), vz = S2(cc[2], x2);
         double v = A2(A2(A2(1.0, M2(lx, vx)), M2(ly, vy)), M2(lz, vz));
         v = A2(__ddiv_rn(v, denom), 0.0);

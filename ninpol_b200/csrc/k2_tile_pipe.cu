@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(T, MINB) k_tile_pipe(TileArgs a)
                 if (ptr[mid] - eb <= i) lo = mid; else hi = mid;
             }
             s.rid[h][i] = (unsigned char)lo;
-            const double *cc = a.cent + (i64)es[i] * 3;
+            const double *cc = a.cent + (i64)es[i] * NPB_CSTRIDE;
             cp_async_8(&s.cx[h][i + lo], cc);
             cp_async_8(&s.cy[h][i + lo], cc + 1);
             cp_async_8(&s.cz[h][i + lo], cc + 2);

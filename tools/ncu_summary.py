@@ -15,6 +15,8 @@ want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__b
         "sm__inst_executed_pipe_fp64.sum", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum",
+        "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
@@ -27,11 +29,30 @@ want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__b
         "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio", "smsp__cycles_active.avg"]
+def num(x):
+    try:
+        return float(x.replace(",", ""))
+    except ValueError:
+        return None
+
+
 for r in rows[2:]:
     for wname in want:
         if wname in hdr:
             i = hdr.index(wname)
             print(f"{wname} = {r[i]} {units[i]}")
+    # sector-per-request efficiency of the global loads (32-byte sectors fetched per warp-level load request;
+    # 4 = a fully coalesced 128-byte line per request for 4-byte accesses, 32 = one sector per lane)
+    a, b = "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum"
+    if a in hdr and b in hdr:
+        sa, sb = num(r[hdr.index(a)]), num(r[hdr.index(b)])
+        if sa and sb:
+            print(f"derived: global-load sectors per request = {sa / sb:.2f}")
+    a, b = "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum"
+    if a in hdr and b in hdr:
+        sa, sb = num(r[hdr.index(a)]), num(r[hdr.index(b)])
+        if sa and sb:
+            print(f"derived: global-store sectors per request = {sa / sb:.2f}")
     print("----")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] +
                      (["--kernel-id", sys.argv[2]] if len(sys.argv) > 2 else []), capture_output=True, text=True).stdout
