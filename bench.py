@@ -167,18 +167,13 @@ def measured_peaks():
     return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
-def profiled(workload, method):
-    """Per-launch counters of the dominant kernel from the committed ncu capture of this workload (profiles/)."""
+def profiled(kind, method):
+    """Per-node DRAM traffic and counters of the dominant kernel from the committed ncu capture of this mesh family."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     try:
-        d = json.load(open(p))
+        return json.load(open(p)).get(f"{kind}:{method}:per_node", {})
     except Exception:
         return {}
-    out = {}
-    if f"{workload}:{method}" in d:
-        out["traffic"] = d[f"{workload}:{method}"]
-    out.update(d.get(f"{workload}:{method}:counters", {}))
-    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -275,18 +270,19 @@ class Plumbing:
             self.dist.destroy_process_group()
 
 
-def device_step(I, method):
-    """One pass with the result left on the device: plan + kernels (+ NCCL gather when gather = all)."""
-    nnz, fell_back = I._ctx.interpolate_run(method, 1)
+def device_step(I, method, chunks=1):
+    """One pass with the result left on the device: plan + kernels (+ NCCL gather when gather = all; with chunks > 1
+    the broadcast of chunk k runs on its own stream under the kernels of chunk k+1)."""
+    nnz, fell_back = I._ctx.interpolate_run(method, chunks)
     if fell_back:   # an exact-zero weight: the general two-pass path (counts exchanged, scan, emit, gather)
         I._ctx.interpolate_count(method)
         I._ctx.interpolate_fetch(None, None, None, None)
 
 
-def timed_device_steps(I, plumb, method, steps, warmup, sampler=None):
+def timed_device_steps(I, plumb, method, steps, warmup, sampler=None, chunks=1):
     ctx = I._ctx
     for _ in range(warmup):
-        device_step(I, method)
+        device_step(I, method, chunks)
     main_ms, step_ms = [], []
     plumb.barrier()
     ctx.synchronize()
@@ -295,7 +291,7 @@ def timed_device_steps(I, plumb, method, steps, warmup, sampler=None):
     l0 = ctx.launch_count()
     ctx.timer_start()
     for _ in range(steps):
-        device_step(I, method)
+        device_step(I, method, chunks)
         main_ms.append(ctx.timing_or("k2_main", ctx.timing_or("k2")))
         step_ms.append(ctx.timing_or("streamed"))
     ms = ctx.timer_stop()
@@ -355,12 +351,13 @@ def roofline_block(I, method, kernel_ms, lo, hi, share_of, workload):
     nbytes, flops, n_proc = algorithmic_model(I, method, lo, hi)
     peak, peak_src = measured_peaks()
     achieved = nbytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
-    prof = profiled(workload, method)
-    traffic = prof.get("traffic")
+    prof = profiled(WORKLOADS[workload][0] if workload in WORKLOADS else workload, method)
+    traffic = prof["bytes"] * n_proc if "bytes" in prof else None
     out = {"bound": "hbm", "kernel": "k_gls_mf (largest size class)" if method == "gls" else f"k_{method}_tile",
            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-           "traffic": traffic * share_of if traffic is not None else None,
-           "traffic_source": "ncu --set full capture of this workload (profiles/), scaled to this rank's share of the nodes" if traffic is not None else None,
+           "traffic": traffic,
+           "traffic_source": ("DRAM bytes per processed node of the committed `ncu --set full` capture of this kernel on the same mesh family "
+                              "(profiles/roofline_traffic.json) x the processed nodes of the timed launch") if traffic is not None else None,
            "peak_source": peak_src, "algorithmic_bytes_per_launch": nbytes, "kernel_ms": kernel_ms, "processed_nodes_this_rank": n_proc}
     return out, flops, prof
 
@@ -448,8 +445,12 @@ def run_ours(args, rank, world):
     value = n_points / (dev["ms_per_step"] * 1e-3)
     lo, hi = ctx.scalar("row_lo"), ctx.scalar("row_hi")
     roof, flops, prof = roofline_block(I, method, dev["kernel_ms"], lo, hi, (hi - lo) / max(n_points, 1), args.workload)
-    compute_only, k4 = None, None
+    compute_only, k4, overlapped = None, None, None
     if world > 1:
+        ov = timed_device_steps(I, plumb, method, args.steps, 2, None, chunks=4)
+        overlapped = {"value": n_points / (ov["ms_per_step"] * 1e-3), "unit": "nodes/s", "ms_per_step": ov["ms_per_step"],
+                      "note": "same step cut into 4 chunks per rank: the NCCL broadcast of chunk k is issued on its own stream while "
+                              "chunk k+1 computes (the headline value gathers after the last kernel)"}
         k4 = k4_breakdown(I, plumb, method)
         I.set_gather("host")
         co = timed_device_steps(I, plumb, method, args.steps, 2)
@@ -492,6 +493,7 @@ def run_ours(args, rank, world):
     }
     if compute_only:
         line["device_compute_only"] = compute_only
+        line["device_overlapped_gather"] = overlapped
         line["k4"] = k4
     if e2e_all:
         line["e2e_gather_all"] = e2e_all
@@ -500,7 +502,8 @@ def run_ours(args, rank, world):
         ach_tf = flops / (dev["kernel_ms"] * 1e-3) / 1e12 if dev["kernel_ms"] > 0 else 0.0
         line["roofline"]["fp64"] = {
             "achieved_effective": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac_effective": ach_tf / fp64_peak if fp64_peak else None,
-            "pipe_active": prof.get("fp64_pipe_active"), "executed_mflop_per_node": prof.get("executed_mflop_per_node"),
+            "pipe_active": prof.get("counters", {}).get("fp64_pipe_active"), "warps_active": prof.get("counters", {}).get("warps_active"),
+            "executed_mflop_per_node": prof.get("counters", {}).get("executed_mflop_per_node"),
             "flop_model": "EFFECTIVE rate: the dense one-RHS Householder model sum 2mn^2 - 2/3 n^3 + 4mn (m=E+3F+B, n=3E+1) divided by the time; the "
                           "multifrontal kernel executes ~10x fewer FLOPs than that model, so the pipe utilisation (pipe_active, from the committed "
                           "ncu capture) is the hardware-side figure",

@@ -16,10 +16,11 @@ typedef long long i64;
 #define NPB_MX_PF 4
 #define NPB_N_TYPES 8
 #define NPB_MX_EE 12
-// Centroids live on the device as [n_elems, 4] doubles (x, y, z, 0): a 32-byte record never straddles two 32-byte
-// sectors, whereas a 24-byte one does half the time - the per-entry centroid gather is the dominant stream of the
-// IDW / LS kernels and goes from 1.5 to 1 sector per entry.  The export strips the pad.
-#define NPB_CSTRIDE 4
+// Doubles per centroid record on the device.  4 (32-byte records that never straddle two 32-byte sectors, pad
+// stripped at export) was measured on B200 and is SLOWER than the packed 3: the gather misses L2 60 % of the time, so
+// the extra 8 bytes per record cost more DRAM traffic than the straddling saves (IDW 0.685 -> 0.655 of the HBM roofline
+// at 50M tets, LS 0.517 -> 0.502).
+#define NPB_CSTRIDE 3
 
 // element tables (reference utils/point_ordering.yaml via process_mesh, interpolator.pyx:274-330);
 // passed to kernels by value -> lives in the constant bank.

@@ -306,6 +306,7 @@ int npb_export_array(npb_ctx *c, const char *name, void *out, i64 cap)
 {
     i64 ne = c->n_elems, np = c->n_points, nf = c->n_faces;
     if (!strcmp(name, "point_coords")) return export_f64(c, c->coords, np * 3, out, cap);
+    if (!strcmp(name, "centroids") && NPB_CSTRIDE == 3) return export_f64(c, c->centroids, ne * 3, out, cap);
     if (!strcmp(name, "centroids")) {   // device records are [n_elems, NPB_CSTRIDE]: strip the pad
         NpbTmp packed;
         NPB_CUDA(packed.alloc(sizeof(double) * (size_t)ne * 3));

@@ -24,8 +24,12 @@ __global__ void k_centroids(ElemTables tab, const int32_t *__restrict__ inpoel, 
         if (dim > 1) cy = __dadd_rn(cy, __ddiv_rn(x[1], dn));
         if (dim > 2) cz = __dadd_rn(cz, __ddiv_rn(x[2], dn));
     }
-    reinterpret_cast<double2 *>(cent + e * NPB_CSTRIDE)[0] = make_double2(cx, cy);
-    reinterpret_cast<double2 *>(cent + e * NPB_CSTRIDE)[1] = make_double2(cz, 0.0);
+    cent[e * NPB_CSTRIDE + 0] = cx;
+    cent[e * NPB_CSTRIDE + 1] = cy;
+    cent[e * NPB_CSTRIDE + 2] = cz;
+#if NPB_CSTRIDE > 3
+    cent[e * NPB_CSTRIDE + 3] = 0.0;
+#endif
 }
 
 __device__ __forceinline__ float cross_norm_sq(float v1x, float v1y, float v1z, float v2x, float v2y, float v2z,

@@ -101,9 +101,7 @@ __global__ void __launch_bounds__(TILE_T, MINB) k_idw_tile(TileArgs a)
                 if (!s_proc[node]) continue;
                 int e = a.esup[eb + i];
                 s_e[i] = e;
-                const double2 *c2 = reinterpret_cast<const double2 *>(a.cent + (i64)e * NPB_CSTRIDE);
-                const double2 cxy = c2[0];
-                const double cc[3] = {cxy.x, cxy.y, c2[1].x};
+                const double *cc = a.cent + (i64)e * NPB_CSTRIDE;
                 double d0 = __dsub_rn(s_x[3 * node], cc[0]);
                 double dist = __dadd_rn(0.0, __dmul_rn(d0, d0));
                 if (a.dim > 1) {
@@ -132,9 +130,8 @@ __global__ void __launch_bounds__(TILE_T, MINB) k_idw_tile(TileArgs a)
                 for (int v = 0; v < MLP_B; v++) {
                     const int u = u0 + v;
                     if (u < KMAX && ee[u >= KMAX ? 0 : u] >= 0) {
-                        const double2 *c2 = reinterpret_cast<const double2 *>(a.cent + (i64)ee[u >= KMAX ? 0 : u] * NPB_CSTRIDE);
-                        const double2 cxy = c2[0];
-                        c[v][0] = cxy.x; c[v][1] = cxy.y; c[v][2] = c2[1].x;
+                        const double *cc = a.cent + (i64)ee[u >= KMAX ? 0 : u] * NPB_CSTRIDE;
+                        c[v][0] = cc[0]; c[v][1] = cc[1]; c[v][2] = cc[2];
                     }
                 }
 #pragma unroll
@@ -253,9 +250,7 @@ __global__ void __launch_bounds__(TILE_T, MINB) k_ls_tile(TileArgs a)
                 if (!s_proc[node]) continue;
                 int e = a.esup[eb + i];
                 s_e[i] = e;
-                const double2 *c2 = reinterpret_cast<const double2 *>(a.cent + (i64)e * NPB_CSTRIDE);
-                const double2 cxy = c2[0];
-                const double cc[3] = {cxy.x, cxy.y, c2[1].x};
+                const double *cc = a.cent + (i64)e * NPB_CSTRIDE;
                 s_vx[i + node] = S2(cc[0], s_x[3 * node]);
                 s_vy[i + node] = S2(cc[1], s_x[3 * node + 1]);
                 s_vz[i + node] = S2(cc[2], s_x[3 * node + 2]);
@@ -276,9 +271,8 @@ __global__ void __launch_bounds__(TILE_T, MINB) k_ls_tile(TileArgs a)
                 for (int v = 0; v < MLP_B; v++) {
                     const int u = u0 + v;
                     if (u < KMAX && ee[u >= KMAX ? 0 : u] >= 0) {
-                        const double2 *c2 = reinterpret_cast<const double2 *>(a.cent + (i64)ee[u >= KMAX ? 0 : u] * NPB_CSTRIDE);
-                        const double2 cxy = c2[0];
-                        c[v][0] = cxy.x; c[v][1] = cxy.y; c[v][2] = c2[1].x;
+                        const double *cc = a.cent + (i64)ee[u >= KMAX ? 0 : u] * NPB_CSTRIDE;
+                        c[v][0] = cc[0]; c[v][1] = cc[1]; c[v][2] = cc[2];
                     }
                 }
 #pragma unroll
