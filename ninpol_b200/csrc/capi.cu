@@ -72,6 +72,31 @@ NpbTimer::NpbTimer(npb_ctx *c_, const char *n, bool accumulate_) : c(c_), name(n
     cudaEventCreate(&b);
     cudaEventRecord(a, c->stream);
 }
+void NpbTimer::stop_lazy()
+{
+    if (!a) return;
+    cudaEventRecord(b, c->stream);
+    if (c->pending_timers.size() > 64) npb_resolve_timers(c);
+    c->pending_timers.push_back({name, a, b, accumulate});
+    a = b = nullptr;
+}
+
+void npb_resolve_timers(npb_ctx *c)
+{
+    for (auto &p : c->pending_timers) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            if (p.accumulate)
+                c->timings[p.name] += ms;
+            else
+                c->timings[p.name] = ms;
+        }
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    c->pending_timers.clear();
+}
+
 NpbTimer::~NpbTimer()
 {
     if (a) cudaEventDestroy(a);
@@ -264,6 +289,7 @@ extern "C" int npb_destroy(npb_ctx *c)
     if (!c) return NPB_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    npb_resolve_timers(c);
     npb_comm_destroy(c);
     free_mesh(c);
     if (c->wbuf) cudaFree(c->wbuf);
@@ -509,7 +535,7 @@ extern "C" int npb_grid_scalar(npb_ctx *c, const char *name, int64_t *out)
         {"MX_ELEMENTS_PER_FACE", c->mx_epf}, {"MX_FACES_PER_POINT", c->mx_fpp}, {"len_esup", c->len_esup},
         {"len_fsup", c->len_fsup}, {"len_esuf", c->len_esuf}, {"len_psup", c->len_psup},
         {"row_lo", c->lo}, {"row_hi", c->hi}, {"rank", c->rank}, {"world", c->world}, {"sm_count", c->sm_count},
-        {"have_cell_fields", (c->have_perm && c->have_dm) ? 1 : 0}, {"plan_nnz", c->plan_nnz},
+        {"have_cell_fields", (c->have_perm && c->have_dm) ? 1 : 0}, {"plan_nnz", c->plan_nnz}, {"flags_checksum", c->flags_checksum},
     };
     for (auto &e : tbl)
         if (strcmp(e.n, name) == 0) {
@@ -600,10 +626,27 @@ extern "C" int npb_set_cell_field_range(npb_ctx *c, const char *name, const doub
     return NPB_OK;
 }
 
-__global__ void k_flags(const i64 *__restrict__ in, i64 n, uint8_t *__restrict__ out)
+// Both flag kernels also fold WHICH nodes are flagged into a 64-bit checksum (sum of (i + 1) * golden-ratio constant over
+// the flagged nodes, wrapping): the host re-cuts the node partition only when it changes, without a pass over the array.
+#define NPB_FLAG_MIX 0x9E3779B97F4A7C15ull
+static int read_flag_checksum(npb_ctx *c);
+__device__ __forceinline__ void flag_checksum(bool set, i64 i, unsigned long long *sum)
+{
+    unsigned long long v = set ? (unsigned long long)(i + 1) * NPB_FLAG_MIX : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(sum, v);
+}
+
+__global__ void k_flags(const i64 *__restrict__ in, i64 n, uint8_t *__restrict__ out, unsigned long long *__restrict__ sum)
 {
     i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = in[i] != 0 ? 1 : 0;
+    bool set = false;
+    if (i < n) {
+        set = in[i] != 0;
+        out[i] = set ? 1 : 0;
+    }
+    flag_checksum(set, i, sum);
 }
 
 extern "C" int npb_set_point_flags(npb_ctx *c, const int64_t *flag, int64_t n_points)
@@ -623,9 +666,10 @@ extern "C" int npb_set_point_flags(npb_ctx *c, const int64_t *flag, int64_t n_po
     NPB_TRY(npb_ensure(&c->scratch, &c->scratch_cap, sizeof(i64) * (size_t)n_points));
     i64 *tmp = (i64 *)c->scratch;
     NPB_TRY(npb_h2d(c, tmp, flag, sizeof(i64) * n_points));
-    k_flags<<<npb_blocks(n_points, 256), 256, 0, c->stream>>>(tmp, n_points, c->nflag);
+    NPB_CUDA(cudaMemsetAsync(c->counters + 66, 0, sizeof(unsigned long long), c->stream));
+    k_flags<<<npb_blocks(n_points, 256), 256, 0, c->stream>>>(tmp, n_points, c->nflag, (unsigned long long *)(c->counters + 66));
     NPB_LAUNCH(c);
-    NPB_CUDA(cudaStreamSynchronize(c->stream));
+    NPB_TRY(read_flag_checksum(c));
     c->have_flags = true;
     c->counted = false;
     c->plan_kind = 0;     // row lengths depend on the flags
@@ -634,14 +678,26 @@ extern "C" int npb_set_point_flags(npb_ctx *c, const int64_t *flag, int64_t n_po
     return NPB_OK;
 }
 
-__global__ void k_flags_f64(const double *__restrict__ in, i64 n, uint8_t *__restrict__ out)
+__global__ void k_flags_f64(const double *__restrict__ in, i64 n, uint8_t *__restrict__ out, unsigned long long *__restrict__ sum)
 {
     i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    bool set = false;
     if (i < n) {
         double f = in[i];
         // numpy's float64 -> int64 cast truncates toward zero; NaN / inf become INT64_MIN (non-zero)
-        out[i] = (f != f || (long long)f != 0) ? 1 : 0;
+        set = (f != f || (long long)f != 0);
+        out[i] = set ? 1 : 0;
     }
+    flag_checksum(set, i, sum);
+}
+
+static int read_flag_checksum(npb_ctx *c)
+{
+    unsigned long long h = 0;
+    NPB_CUDA(cudaMemcpyAsync(&h, c->counters + 66, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    NPB_CUDA(cudaStreamSynchronize(c->stream));
+    c->flags_checksum = (i64)(h >> 1);     // non-negative for the int64 scalar interface
+    return NPB_OK;
 }
 
 extern "C" int npb_set_point_flags_f64(npb_ctx *c, const double *flag, int64_t n_points)
@@ -658,9 +714,11 @@ extern "C" int npb_set_point_flags_f64(npb_ctx *c, const double *flag, int64_t n
     NPB_CUDA(cudaSetDevice(c->device));
     NPB_TRY(npb_ensure(&c->scratch, &c->scratch_cap, sizeof(double) * (size_t)n_points));
     NPB_TRY(npb_h2d(c, c->scratch, flag, sizeof(double) * n_points));
-    k_flags_f64<<<npb_blocks(n_points, 256), 256, 0, c->stream>>>((const double *)c->scratch, n_points, c->nflag);
+    NPB_CUDA(cudaMemsetAsync(c->counters + 66, 0, sizeof(unsigned long long), c->stream));
+    k_flags_f64<<<npb_blocks(n_points, 256), 256, 0, c->stream>>>((const double *)c->scratch, n_points, c->nflag,
+                                                                  (unsigned long long *)(c->counters + 66));
     NPB_LAUNCH(c);
-    NPB_CUDA(cudaStreamSynchronize(c->stream));
+    NPB_TRY(read_flag_checksum(c));
     c->have_flags = true;
     c->counted = false;
     c->plan_kind = 0;     // row lengths depend on the flags
@@ -729,6 +787,7 @@ extern "C" int npb_interpolate_count(npb_ctx *c, int method, int64_t *nnz)
             }
         }
         tm.stop();
+        npb_resolve_timers(c);
         if (method != NPB_METHOD_GLS && !c->timings.count("k2_main")) c->timings["k2_main"] = c->timings["k2"];
     }
     {
@@ -918,6 +977,7 @@ extern "C" int npb_interpolate_dense(npb_ctx *c, int method, double *weights, do
 extern "C" int npb_timing(npb_ctx *c, const char *name, double *ms)
 {
     if (!c || !name || !ms) return NPB_ERR_ARG;
+    npb_resolve_timers(c);
     auto it = c->timings.find(name);
     if (it == c->timings.end()) {
         npb_set_error("npb_timing: no timing named '%s'", name);

@@ -54,7 +54,14 @@ void npb_set_error(const char *fmt, ...);
 
 struct NcclApi;  // k4_shard.cu
 
+struct NpbPendingTimer {
+    std::string name;
+    cudaEvent_t a, b;
+    bool accumulate;
+};
+
 struct npb_ctx {
+    std::vector<NpbPendingTimer> pending_timers;
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
@@ -90,6 +97,7 @@ struct npb_ctx {
     double *perm = nullptr, *diff_mag = nullptr;
     uint8_t *nflag = nullptr;
     bool have_perm = false, have_dm = false, have_flags = false;
+    i64 flags_checksum = 0;      // which nodes are flagged, folded on the device (capi.cu)
 
     // ---- partition / communicator ----
     int rank = 0, world = 1;
@@ -151,6 +159,8 @@ struct NpbTimer {
     cudaEvent_t a, b;
     bool accumulate;
     NpbTimer(npb_ctx *c_, const char *n, bool accumulate_ = false);   // accumulate: add to timings[name]
+    void stop_lazy();   // records the closing event only; the elapsed time is read when somebody asks (npb_resolve_timers):
+                        // no host synchronisation on the hot path
     ~NpbTimer();   // an early (error) return must not leak the two events
     NpbTimer(const NpbTimer &) = delete;
     NpbTimer &operator=(const NpbTimer &) = delete;
@@ -175,6 +185,7 @@ int npb_ensure_out(npb_ctx *c, size_t n);
 int npb_k2_gls(npb_ctx *c, i64 lo, i64 hi);
 int npb_k3_fill(npb_ctx *c, i64 lo, i64 hi);
 int npb_read_int(npb_ctx *c, const int *d_src, int *h_out);
+void npb_resolve_timers(npb_ctx *c);   // turns the lazily stopped timers into timings[] entries (waits for their events)
 __global__ void k_copy2_int(int *dst, const int *src);   // capi.cu: two ints, device -> mapped host block
 __global__ void k_copy_int(int *dst, const int *src);    // capi.cu   // device int -> host through the mapped block + stream sync
 int npb_minmax_i32(npb_ctx *c, const int32_t *in, i64 n, int32_t *h_min, int32_t *h_max);

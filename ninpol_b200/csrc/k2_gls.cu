@@ -1129,6 +1129,7 @@ k_gls_mf(GlsArgs a, const int32_t *__restrict__ list, int count, int *__restrict
 int npb_k2_gls(npb_ctx *c, i64 lo, i64 hi)
 {
     if (hi <= lo) return NPB_OK;
+    npb_resolve_timers(c);   // a lazily stopped "k2_main" of an earlier IDW / LS launch must not land on top of this pass's
     cudaStream_t s = c->stream;
     GlsArgs a;
     a.esup_ptr = c->esup_ptr; a.esup = c->esup; a.fsup_ptr = c->fsup_ptr; a.fsup = c->fsup; a.esuf2 = c->esuf2;

@@ -431,7 +431,7 @@ static int tile_launch(npb_ctx *c, const TileArgs &a, int method)
     }
     NPB_LAUNCH(c);
     NPB_CUDA(cudaGetLastError());
-    tm.stop();
+    tm.stop_lazy();     // no host synchronisation between the tile kernel and whatever follows it on the stream
     return NPB_OK;
 }
 

@@ -22,7 +22,7 @@
 #include <stdlib.h>
 #include "gls_common.cuh"
 
-int npb_k4_share_flags(npb_ctx *c, int mine, int *any);
+int npb_k4_share_flags(npb_ctx *c, const int *d_bad2, int host_flag, int *any);
 int npb_k4_bcast_chunk(npb_ctx *c, cudaStream_t st, const std::vector<i64> &node_lo, const std::vector<i64> &node_hi,
                        const std::vector<i64> &nz_lo, const std::vector<i64> &nz_hi, bool with_neumann);
 int npb_k2_idw_ls_direct(npb_ctx *c, int method, i64 lo, i64 hi, int *used);
@@ -275,13 +275,17 @@ static int run_pipeline(npb_ctx *c, int method, int K, const double *perm_host, 
         NPB_CUDA(cudaEventRecord(ev_side, side));
         NPB_CUDA(cudaStreamWaitEvent(s, ev_side, 0));
     }
-    // verdict: exact zeros / mismatches on this rank, shared with the peers
-    k_copy2_int<<<1, 1, 0, s>>>(c->d_small + 10, bad);
-    NPB_LAUNCH(c);
-    NPB_CUDA(cudaStreamSynchronize(s));
-    int mine = (c->h_small[10] != 0 || c->h_small[11] != 0 || !tiles_ok) ? 1 : 0;
-    int any = mine;
-    if (W > 1) NPB_TRY(npb_k4_share_flags(c, mine, &any));
+    // verdict: exact zeros / mismatches on this rank, shared with the peers (world > 1: the device-side counters go
+    // straight into the all-reduce, one host synchronisation for the whole step)
+    int any = tiles_ok ? 0 : 1;
+    if (W > 1) {
+        NPB_TRY(npb_k4_share_flags(c, bad, any, &any));
+    } else {
+        k_copy2_int<<<1, 1, 0, s>>>(c->d_small + 10, bad);
+        NPB_LAUNCH(c);
+        NPB_CUDA(cudaStreamSynchronize(s));
+        if (c->h_small[10] != 0 || c->h_small[11] != 0) any = 1;
+    }
     if (any) {
         *fell_back = 1;
         c->plan_failed[method] = true;

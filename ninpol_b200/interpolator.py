@@ -93,14 +93,16 @@ class _PinnedPool:
         dtype = np.dtype(dtype)
         free = None
         for owner in self._blocks.setdefault(name, []):
-            # references: the list, the loop variable and getrefcount's argument; a live view adds one
-            if owner.dtype == dtype and owner.size >= n and sys.getrefcount(owner) <= 3:
+            # references: the list, the loop variable and getrefcount's argument; a live view adds one.  A block more
+            # than twice the request is not used: scipy copies index / data arrays that are views of a base more than
+            # twice their size (sparse._sputils._prune_array), which would cost a full host copy per call
+            if owner.dtype == dtype and n <= owner.size <= 2 * n + 64 and sys.getrefcount(owner) <= 3:
                 if free is None or owner.size < free.size:
                     free = owner
         if free is None:
             free = _capi.pinned_empty(n + n // 16 + 16, dtype)
             # keep at most two idle generations per name: drop smaller unused blocks
-            self._blocks[name] = [o for o in self._blocks[name] if sys.getrefcount(o) > 3 or o.size >= n][-3:]
+            self._blocks[name] = [o for o in self._blocks[name] if sys.getrefcount(o) > 3 or n <= o.size <= 2 * n + 64][-3:]
             self._blocks[name].append(free)
         return free[:n]
 
@@ -300,6 +302,7 @@ class Interpolator:
             self.logger.log(f"Data loaded in {time.time() - t0:.2f} seconds")
             self.last_timings["load_mesh_data_s"] = time.time() - t0
         self.is_grid_initialized = True
+        self._pool.clear()        # blocks sized for the previous mesh (results still held by the caller stay alive)
         for reg in self._registered.values():
             reg.release()
         self._registered = {}
@@ -525,11 +528,12 @@ class Interpolator:
         self._flags_host = flags
         h2d = flags.nbytes
         if self.comm.world > 1:
-            # the node ranges depend on WHICH nodes are flagged (skipped nodes cost nothing): re-cut them only when
-            # that set changed - cutting is a few numpy passes over all nodes, 150 ms at 8.5M nodes
-            mask = flags != 0
-            if self._flag_mask is None or mask.shape != self._flag_mask.shape or not np.array_equal(mask, self._flag_mask):
-                self._flag_mask = mask
+            # the node ranges depend on WHICH nodes are flagged (skipped nodes cost nothing): re-cut them only when that
+            # set changed - cutting is a few numpy passes over all nodes, 150 ms at 8.5M nodes.  The flag kernel folds
+            # the set into a 64-bit checksum on the device, so the test costs no pass over the array either.
+            checksum = (self._ctx.scalar("flags_checksum"), int(flags.shape[0]))
+            if checksum != self._flag_mask:
+                self._flag_mask = checksum
                 self._flag_version += 1
         self._set_partition(method)
         fields = None

@@ -262,3 +262,5 @@ def test_pinned_pool_reuses_a_block_only_when_unreferenced(monkeypatch):
         e = P.take("data", 100, np.float64)
         del e
     assert len(allocs) == 3
+    small = P.take("data", 10, np.float64)       # a block more than twice the request is never handed out:
+    assert len(allocs) == 4 and small.base.size <= 2 * 10 + 64   # scipy would copy such a view
