@@ -1151,20 +1151,22 @@ int npb_k2_gls(npb_ctx *c, i64 lo, i64 hi)
     const int force_dense = ((force && force[0] == '1') || c->dim == 2) ? 1 : 0;
     k_gls_classify<<<npb_blocks(nloc, 256), 256, 0, s>>>(a, lo, hi, cls, force_dense);
     NPB_LAUNCH(c);
-    {   // experiments: NPB_GLS_FCAP="class:doubles[,class:doubles...]" overrides the front sizes
-        static bool once = false;
+    {   // experiments: NPB_GLS_FCAP="class:doubles[,class:doubles...]" overrides the front sizes (re-read every pass)
+        static const MfClass defaults[MF_NCLASS] = MF_CLASS_TABLE;
+        MfClass want[MF_NCLASS];
+        memcpy(want, defaults, sizeof(want));
         const char *fo = getenv("NPB_GLS_FCAP");
-        if (!once && fo) {
-            once = true;
-            for (const char *q = fo; q && *q;) {
-                int k = atoi(q);
-                const char *col = strchr(q, ':');
-                if (!col) break;
-                if (k >= 1 && k < MF_NCLASS - 1) h_mf[k].fcap = atoi(col + 1);
-                q = strchr(col, ',');
-                if (q) q++;
-            }
-            NPB_CUDA(cudaMemcpyToSymbol(c_mf, h_mf, sizeof(h_mf)));
+        for (const char *q = fo; q && *q;) {
+            int k = atoi(q);
+            const char *col = strchr(q, ':');
+            if (!col) break;
+            if (k >= 1 && k < MF_NCLASS - 1 && atoi(col + 1) >= 256) want[k].fcap = atoi(col + 1);
+            q = strchr(col, ',');
+            if (q) q++;
+        }
+        if (memcmp(want, h_mf, sizeof(want)) != 0) {
+            memcpy(h_mf, want, sizeof(want));
+            NPB_CUDA(cudaMemcpyToSymbolAsync(c_mf, h_mf, sizeof(h_mf), 0, cudaMemcpyHostToDevice, s));
         }
     }
     // test / A-B switches, read once per pass (the tests flip them between calls of one process)
