@@ -237,20 +237,53 @@ k_esuel_star(ElemTables tab, const int32_t *__restrict__ inpoel, const uint8_t *
     __shared__ unsigned short s_ij[STAR_WARPS][STAR_PAIRS];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
-    for (i64 p = (i64)blockIdx.x * STAR_WARPS + wid; p < n_points; p += (i64)gridDim.x * STAR_WARPS) {
-        const int eb = esup_ptr[p], E = esup_ptr[p + 1] - eb;
+    // The three dependent loads of a star (esup_ptr -> esup ids -> connectivity rows) are software-pipelined over the
+    // nodes a warp visits: the row pointer is fetched two nodes ahead, the element ids one node ahead (two per lane:
+    // STAR_CAPE = 64), so only the connectivity rows are waited for.
+    const i64 step = (i64)gridDim.x * STAR_WARPS;
+    const i64 p_first = (i64)blockIdx.x * STAR_WARPS + wid;
+    int ebC = 0, EC = 0, eC0 = -1, eC1 = -1, ebB = 0, EB = 0;
+    if (p_first < n_points) {
+        ebC = esup_ptr[p_first];
+        EC = esup_ptr[p_first + 1] - ebC;
+        if (EC <= STAR_CAPE) {
+            eC0 = lane < EC ? esup[ebC + lane] : -1;
+            eC1 = lane + 32 < EC ? esup[ebC + 32 + lane] : -1;
+        }
+    }
+    if (p_first + step < n_points) {
+        ebB = esup_ptr[p_first + step];
+        EB = esup_ptr[p_first + step + 1] - ebB;
+    }
+    for (i64 p = p_first; p < n_points; p += step) {
+        const int eb = ebC, E = EC, e0 = eC0, e1 = eC1;
+        (void)eb;
+        // next node's element ids, the node after's row pointer
+        int eN0 = -1, eN1 = -1, ebA = 0, EA = 0;
+        if (p + step < n_points && EB <= STAR_CAPE) {
+            eN0 = lane < EB ? esup[ebB + lane] : -1;
+            eN1 = lane + 32 < EB ? esup[ebB + 32 + lane] : -1;
+        }
+        if (p + 2 * step < n_points) {
+            ebA = esup_ptr[p + 2 * step];
+            EA = esup_ptr[p + 2 * step + 1] - ebA;
+        }
+        ebC = ebB; EC = EB; eC0 = eN0; eC1 = eN1; ebB = ebA; EB = EA;
         if (E > STAR_CAPE) {
             if (lane == 0) atomicExch(too_big, 1);
             continue;
         }
         __syncwarp();
-        for (int i = lane; i < E; i += 32) {
-            const int e = esup[eb + i];
-            s_es[wid][i] = e;
-            s_type[wid][i] = etype[e];
-            const int4 *rp = reinterpret_cast<const int4 *>(inpoel + (i64)e * SPE);
 #pragma unroll
-            for (int v = 0; v < SPE / 4; v++) reinterpret_cast<int4 *>(&s_conn[wid][i * SPE])[v] = rp[v];
+        for (int h = 0; h < 2; h++) {
+            const int e = h == 0 ? e0 : e1, i = lane + 32 * h;
+            if (e >= 0) {
+                s_es[wid][i] = e;
+                s_type[wid][i] = etype[e];
+                const int4 *rp = reinterpret_cast<const int4 *>(inpoel + (i64)e * SPE);
+#pragma unroll
+                for (int v = 0; v < SPE / 4; v++) reinterpret_cast<int4 *>(&s_conn[wid][i * SPE])[v] = rp[v];
+            }
         }
         __syncwarp();
         // sides (element i, local face j) whose smallest node is p, compacted
