@@ -102,9 +102,16 @@ static int ensure_chunk_table(npb_ctx *c, int K)
     if (c->plan_chunks == K && (int)c->chunk_node.size() == c->world * K + 1) return NPB_OK;
     const int W = c->world;
     c->chunk_node.assign((size_t)W * K + 1, 0);
+    // Chunk sizes ramp up and down (weights 1, 2, 3, 3, ..., 3, 2): the upload of the first chunk and the download of
+    // the last one are the two legs nothing can hide, so those chunks are the small ones.  Same rule on every rank.
+    std::vector<i64> cum(K + 1, 0);
+    for (int k = 0; k < K; k++) {
+        const i64 wgt = K < 4 ? 1 : (k == 0 ? 1 : (k == 1 || k == K - 1) ? 2 : 3);
+        cum[k + 1] = cum[k] + wgt;
+    }
     for (int r = 0; r < W; r++) {
         const i64 a = c->bounds[r], n = c->bounds[r + 1] - a;
-        for (int k = 0; k < K; k++) c->chunk_node[(size_t)r * K + k] = a + (n * k) / K;
+        for (int k = 0; k < K; k++) c->chunk_node[(size_t)r * K + k] = a + (n * cum[k]) / cum[K];
     }
     c->chunk_node[(size_t)W * K] = c->n_points;
     // one gather kernel would do; the table is tiny (W*K+1 <= 16*64+1) and read once per plan
