@@ -296,6 +296,8 @@ extern "C" int npb_destroy(npb_ctx *c)
     if (c->indices) cudaFree(c->indices);
     if (c->data) cudaFree(c->data);
     if (c->scratch) cudaFree(c->scratch);
+    if (c->scan_tmp) cudaFree(c->scan_tmp);
+    if (c->part_tmp) cudaFree(c->part_tmp);
     if (c->gls_ws) cudaFree(c->gls_ws);
     if (c->counters) cudaFree(c->counters);
     if (c->h_small) cudaFreeHost(c->h_small);

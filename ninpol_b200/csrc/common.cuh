@@ -124,8 +124,10 @@ struct npb_ctx {
     int32_t *indices = nullptr;
     double *data = nullptr;
     size_t out_cap = 0;
-    void *scratch = nullptr;     // scan / select temp storage
+    void *scratch = nullptr;     // staging of flag uploads, rebased indptr, edge sort temp storage
     size_t scratch_cap = 0;
+    void *scan_tmp = nullptr, *part_tmp = nullptr;   // tile totals of the scans; per-block class histograms
+    size_t scan_tmp_cap = 0, part_tmp_cap = 0;
     int32_t *node_list = nullptr;  // GLS work lists
     void *gls_ws = nullptr;
     size_t gls_ws_cap = 0;
@@ -170,7 +172,7 @@ struct NpbTimer {
 // ---- scan.cu (CUB) ----
 int npb_exclusive_scan_i32(npb_ctx *c, const int32_t *in, int32_t *out, i64 n);   // out may alias in
 int npb_max_i32(npb_ctx *c, const int32_t *in, i64 n, int32_t *host_out);
-int npb_select_class(npb_ctx *c, const uint8_t *cls, i64 lo, i64 hi, int which, int32_t *out, int *host_count);
+int npb_partition_classes(npb_ctx *c, const uint8_t *cls, i64 lo, i64 hi, int32_t *out, int *host_starts /*[9 + 1]*/);
 int npb_sort_pairs_u32(npb_ctx *c, const uint32_t *keys_in, uint32_t *keys_out, const uint32_t *vals_in, uint32_t *vals_out, i64 n);
 int npb_propagate_heads(npb_ctx *c, uint2 *pairs, i64 n);
 

@@ -1141,7 +1141,7 @@ int npb_k2_gls(npb_ctx *c, i64 lo, i64 hi)
         // [0, n): work list of the current class; [n, 2n): overflow list; then n bytes of classes
         NPB_TRY(npb_alloc(c, (void **)&c->node_list, sizeof(int32_t) * 2 * (size_t)c->n_points + (size_t)c->n_points));
     }
-    int32_t *list = c->node_list, *overflow = c->node_list + c->n_points;
+    int32_t *overflow = c->node_list + c->n_points;
     uint8_t *cls = (uint8_t *)(c->node_list + 2 * c->n_points);
     int *n_overflow = c->counters + 40;
     NPB_CUDA(cudaMemsetAsync(n_overflow, 0, sizeof(int), s));
@@ -1180,10 +1180,13 @@ int npb_k2_gls(npb_ctx *c, i64 lo, i64 hi)
     static const char *cls_names[MF_NCLASS] = {"", "k2_gls_c1", "k2_gls_c2", "k2_gls_c3", "k2_gls_c4", "k2_gls_c5", "k2_gls_c6", "k2_gls_c7", "k2_gls_dense"};
     for (int k = 1; k < MF_NCLASS; k++) c->timings.erase(cls_names[k]);
     int n_dense_direct = 0;
+    // work lists of all classes at once: a stable partition of [lo, hi) by class (scan.cu), one host round trip
+    int starts[MF_NCLASS + 1];
+    NPB_TRY(npb_partition_classes(c, cls, lo, hi, c->node_list, starts));
     for (int k = 1; k < MF_NCLASS - 1; k++) {
-        int count = 0;
-        NPB_TRY(npb_select_class(c, cls, lo, hi, k, list, &count));
+        const int count = starts[k + 1] - starts[k];
         if (count == 0) continue;
+        const int32_t *list = c->node_list + starts[k];
         int *counter = c->counters + 20 + k;
         NPB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), s));
         NpbTimer tk(c, cls_names[k]);
@@ -1218,8 +1221,8 @@ int npb_k2_gls(npb_ctx *c, i64 lo, i64 hi)
     // dense fallback: stars classified as too large, then whatever overflowed at run time
     {
         NpbTimer tk(c, cls_names[MF_NCLASS - 1]);
-        NPB_TRY(npb_select_class(c, cls, lo, hi, MF_NCLASS - 1, list, &n_dense_direct));
-        NPB_TRY(npb_gls_dense(c, a, list, n_dense_direct));
+        n_dense_direct = starts[MF_NCLASS] - starts[MF_NCLASS - 1];
+        NPB_TRY(npb_gls_dense(c, a, c->node_list + starts[MF_NCLASS - 1], n_dense_direct));
         int h_over = 0;
         NPB_TRY(npb_read_int(c, n_overflow, &h_over));
         NPB_TRY(npb_gls_dense(c, a, overflow, h_over));
