@@ -288,14 +288,14 @@ k_esuel_star(ElemTables tab, const int32_t *__restrict__ inpoel, const uint8_t *
         __syncwarp();
         // sides (element i, local face j) whose smallest node is p, compacted
         int P = 0;
-        const int total = E * NPB_MX_FE;
+        const int total = E * sfe;      // sfe = 4 or 6: the most local faces an element of this mesh has
         for (int idx0 = 0; idx0 < total; idx0 += 32) {
             const int idx = idx0 + lane;
             bool ok = false;
             int k0 = -1, k1 = -1, k2 = -1, i = 0, j = 0;
             if (idx < total) {
-                i = idx / NPB_MX_FE;
-                j = idx - i * NPB_MX_FE;
+                i = idx / sfe;
+                j = idx - i * sfe;
                 const int t = s_type[wid][i];
                 if (j < tab.nfael[t]) {
                     const int nj = tab.lnofa[t][j];
@@ -337,7 +337,21 @@ k_esuel_star(ElemTables tab, const int32_t *__restrict__ inpoel, const uint8_t *
             P += __popc(bal);
         }
         __syncwarp();
-        // pair the sides: side a looks for the first later side b with the same node set and writes both entries
+        // pair the sides.  Up to 32 of them (every star of the BASELINE meshes): one side per lane, the lanes holding the
+        // same node set find each other with three __match_any_sync, each side writes its own entry.  More: side a looks
+        // for the first later side b with the same node set and writes both entries.
+        if (P <= 32) {
+            const bool live = lane < P;
+            const int k0 = live ? s_key[wid][lane][0] : -2 - lane, k1 = live ? s_key[wid][lane][1] : -2 - lane,
+                      k2 = live ? s_key[wid][lane][2] : -2 - lane;
+            const unsigned peers = __match_any_sync(FULL, k0) & __match_any_sync(FULL, k1) & __match_any_sync(FULL, k2);
+            const unsigned others = peers & ~(1u << lane);
+            if (live && others) {
+                const int ija = s_ij[wid][lane], ijb = s_ij[wid][__ffs(others) - 1];
+                const int ea = s_es[wid][ija >> 3], eb2 = s_es[wid][ijb >> 3];
+                if (ea != eb2) esuel[(i64)ea * sfe + (ija & 7)] = eb2;
+            }
+        } else
         for (int a0 = 0; a0 < P; a0 += 32) {
             const int a = a0 + lane;
             if (a < P) {

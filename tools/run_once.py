@@ -9,7 +9,7 @@ from ninpol_b200 import meshgen
 kind, n, method = sys.argv[1], int(sys.argv[2]), sys.argv[3]
 rep = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 mesh = meshgen.make_case(kind, n)
-I = ninpol_b200.Interpolator()
+I = ninpol_b200.Interpolator(stream_chunks=int(os.environ.get("RUN_ONCE_CHUNKS", "8")))   # 1: one launch per kernel over all nodes
 I.load_mesh(mesh_obj=mesh)
 for meth in method.split(","):
     for _ in range(rep):
