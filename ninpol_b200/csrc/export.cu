@@ -199,10 +199,9 @@ static int build_edges(npb_ctx *c)
         npb_set_error("edge table too large for 32-bit slots");
         return NPB_ERR_RANGE;
     }
-    int32_t *ebase = nullptr, *flag = nullptr;
-    uint32_t *keys = nullptr, *slots = nullptr, *skeys = nullptr, *sslots = nullptr;
-    uint2 *pairs = nullptr;
-    NPB_CUDA(cudaMalloc(&ebase, sizeof(int32_t) * (ne + 1)));
+    NpbTmp t_ebase, t_flag, t_keys, t_slots, t_skeys, t_sslots, t_pairs;   // freed on every return path
+    NPB_CUDA(t_ebase.alloc(sizeof(int32_t) * (ne + 1)));
+    int32_t *ebase = t_ebase.as<int32_t>();
     k_edge_count<<<npb_blocks(ne + 1, 256), 256, 0, s>>>(c->etab, c->etype, ne, ebase);
     NPB_LAUNCH(c);
     NPB_TRY(npb_exclusive_scan_i32(c, ebase, ebase, ne + 1));
@@ -210,12 +209,16 @@ static int build_edges(npb_ctx *c)
     NPB_CUDA(cudaMemcpyAsync(&total, ebase + ne, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     NPB_CUDA(cudaStreamSynchronize(s));
     size_t n1 = (size_t)(total > 0 ? total : 1);
-    NPB_CUDA(cudaMalloc(&keys, 4 * n1));
-    NPB_CUDA(cudaMalloc(&slots, 4 * n1));
-    NPB_CUDA(cudaMalloc(&skeys, 4 * n1));
-    NPB_CUDA(cudaMalloc(&sslots, 4 * n1));
-    NPB_CUDA(cudaMalloc(&pairs, 8 * n1));
-    NPB_CUDA(cudaMalloc(&flag, sizeof(int32_t) * (size_t)(nslots + 1)));
+    NPB_CUDA(t_keys.alloc(4 * n1));
+    NPB_CUDA(t_slots.alloc(4 * n1));
+    NPB_CUDA(t_skeys.alloc(4 * n1));
+    NPB_CUDA(t_sslots.alloc(4 * n1));
+    NPB_CUDA(t_pairs.alloc(8 * n1));
+    NPB_CUDA(t_flag.alloc(sizeof(int32_t) * (size_t)(nslots + 1)));
+    uint32_t *keys = t_keys.as<uint32_t>(), *slots = t_slots.as<uint32_t>();
+    uint32_t *skeys = t_skeys.as<uint32_t>(), *sslots = t_sslots.as<uint32_t>();
+    uint2 *pairs = t_pairs.as<uint2>();
+    int32_t *flag = t_flag.as<int32_t>();
     NPB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t) * (size_t)(nslots + 1), s));
     NPB_TRY(npb_alloc(c, (void **)&c->inedel_d, sizeof(i64) * (size_t)nslots));
     k_fill_i64<<<npb_blocks(nslots, 256), 256, 0, s>>>(c->inedel_d, nslots, -1);
@@ -240,7 +243,6 @@ static int build_edges(npb_ctx *c)
         NPB_LAUNCH(c);
     }
     NPB_CUDA(cudaStreamSynchronize(s));
-    cudaFree(ebase); cudaFree(flag); cudaFree(keys); cudaFree(slots); cudaFree(skeys); cudaFree(sslots); cudaFree(pairs);
     return NPB_OK;
 }
 
@@ -272,15 +274,14 @@ static int out_i64(npb_ctx *c, const i64 *dev, i64 n, void *out, i64 cap)
 static int export_rows(npb_ctx *c, const int32_t *src, i64 rows, int ss, int ds, void *out, i64 cap)
 {
     i64 n = rows * ds;
-    i64 *tmp = nullptr;
-    NPB_CUDA(cudaMalloc(&tmp, sizeof(i64) * (size_t)(n > 0 ? n : 1)));
+    NpbTmp t;
+    NPB_CUDA(t.alloc(sizeof(i64) * (size_t)(n > 0 ? n : 1)));
+    i64 *tmp = t.as<i64>();
     if (n > 0) {
         k_widen_rows<<<npb_blocks(n, 256), 256, 0, c->stream>>>(src, rows, ss, ds, tmp);
         NPB_LAUNCH(c);
     }
-    int rc = out_i64(c, tmp, n, out, cap);
-    cudaFree(tmp);
-    return rc;
+    return out_i64(c, tmp, n, out, cap);
 }
 
 __global__ void k_strip_pad(const double *__restrict__ in, i64 n, double *__restrict__ out)
@@ -344,19 +345,19 @@ int npb_export_array(npb_ctx *c, const char *name, void *out, i64 cap)
     if (!strcmp(name, "element_types") || !strcmp(name, "boundary_faces") || !strcmp(name, "boundary_points")) {
         const uint8_t *src = !strcmp(name, "element_types") ? c->etype : (!strcmp(name, "boundary_faces") ? c->bface : c->bpoint);
         i64 n = !strcmp(name, "element_types") ? ne : (!strcmp(name, "boundary_faces") ? nf : np);
-        i64 *tmp = nullptr;
-        NPB_CUDA(cudaMalloc(&tmp, sizeof(i64) * (size_t)(n > 0 ? n : 1)));
+        NpbTmp t;
+        NPB_CUDA(t.alloc(sizeof(i64) * (size_t)(n > 0 ? n : 1)));
+        i64 *tmp = t.as<i64>();
         if (n > 0) {
             k_widen_u8<<<npb_blocks(n, 256), 256, 0, c->stream>>>(src, n, tmp);
             NPB_LAUNCH(c);
         }
-        int rc = out_i64(c, tmp, n, out, cap);
-        cudaFree(tmp);
-        return rc;
+        return out_i64(c, tmp, n, out, cap);
     }
     if (!strcmp(name, "esuf") || !strcmp(name, "esuf_ptr")) {
-        int32_t *ptr = nullptr;
-        NPB_CUDA(cudaMalloc(&ptr, sizeof(int32_t) * (size_t)(nf + 1)));
+        NpbTmp t_ptr, t_flat;
+        NPB_CUDA(t_ptr.alloc(sizeof(int32_t) * (size_t)(nf + 1)));
+        int32_t *ptr = t_ptr.as<int32_t>();
         k_esuf_count<<<npb_blocks(nf + 1, 256), 256, 0, c->stream>>>(c->esuf2, nf, ptr);
         NPB_LAUNCH(c);
         int rc = npb_exclusive_scan_i32(c, ptr, ptr, nf + 1);
@@ -364,17 +365,15 @@ int npb_export_array(npb_ctx *c, const char *name, void *out, i64 cap)
             if (!strcmp(name, "esuf_ptr")) {
                 rc = export_rows(c, ptr, nf + 1, 1, 1, out, cap);
             } else {
-                i64 *tmp = nullptr;
-                NPB_CUDA(cudaMalloc(&tmp, sizeof(i64) * (size_t)(c->len_esuf > 0 ? c->len_esuf : 1)));
+                NPB_CUDA(t_flat.alloc(sizeof(i64) * (size_t)(c->len_esuf > 0 ? c->len_esuf : 1)));
+                i64 *tmp = t_flat.as<i64>();
                 if (nf > 0) {
                     k_esuf_flat<<<npb_blocks(nf, 256), 256, 0, c->stream>>>(c->esuf2, ptr, nf, tmp);
                     NPB_LAUNCH(c);
                 }
                 rc = out_i64(c, tmp, c->len_esuf, out, cap);
-                cudaFree(tmp);
             }
         }
-        cudaFree(ptr);
         return rc;
     }
     npb_set_error("npb_grid_array: unknown or unavailable array '%s'", name);
