@@ -6,7 +6,7 @@ $B > gpurun_out/r02_prof_plain.json 2> gpurun_out/r02_prof_plain.err &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r02_launches_bench_c4.csv $B > gpurun_out/r02_prof_ncu.json 2> gpurun_out/r02_prof_ncu.err
 echo "launch list rc=$?"
 RUN_ONCE_CHUNKS=1 python tools/run_once.py tet 100 gls > gpurun_out/r02_prof_gls_plain.log 2>&1 &&
-RUN_ONCE_CHUNKS=1 ncu --set full --clock-control none --import-source on -k regex:"k_gls_mf<12>" -c 1 -o gpurun_out/r02_prof_gls python tools/run_once.py tet 100 gls > gpurun_out/r02_prof_gls_ncu.log 2>&1
+RUN_ONCE_CHUNKS=1 ncu --set full --clock-control none --import-source on -k regex:k_gls_mf -c 3 -o gpurun_out/r02_prof_gls python tools/run_once.py tet 100 gls > gpurun_out/r02_prof_gls_ncu.log 2>&1
 echo "gls capture rc=$?"
 RUN_ONCE_CHUNKS=1 python tools/run_once.py tet 120 idw,ls > gpurun_out/r02_prof_tiles_plain.log 2>&1 &&
 RUN_ONCE_CHUNKS=1 ncu --set full --clock-control none --import-source on -k regex:"k_idw_tile|k_ls_tile|k_tile_pipe" -c 2 -o gpurun_out/r02_prof_tiles python tools/run_once.py tet 120 idw,ls > gpurun_out/r02_prof_tiles_ncu.log 2>&1
