@@ -175,6 +175,10 @@ int npb_interpolate_streamed(npb_ctx *ctx, int method, int n_chunks, const doubl
 int npb_timing(npb_ctx *ctx, const char *name, double *ms);
 /* Number of this library's kernel launches since the context was created (bench.py's gpu_launches). */
 int npb_launch_count(npb_ctx *ctx, int64_t *count);
+/* Debug aid (no reference counterpart): with NPB_DEBUG_GUARDS=1 in the environment when the library is first used,
+ * every device block the library allocates is followed by 64 guard bytes; this reads them all back.  n_blocks = guarded
+ * blocks checked, n_damaged = blocks whose guard was overwritten (npb_last_error names one).  Both 0 when guards are off. */
+int npb_check_guards(npb_ctx *ctx, int64_t *n_blocks, int64_t *n_damaged);
 
 /* Measurement helpers used by bench.py for the roofline denominators that MEASURED_PEAKS.json lacks:
  * a register-resident DFMA loop (FP64 TFLOP/s) and a device copy (GB/s, read+write). */

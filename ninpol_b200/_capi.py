@@ -44,6 +44,7 @@ _SIGNATURES = {
     "npb_interpolate_streamed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 6 + [ctypes.c_int64, _c_i64p]),
     "npb_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]),
     "npb_launch_count": (ctypes.c_int, [ctypes.c_void_p, _c_i64p]),
+    "npb_check_guards": (ctypes.c_int, [ctypes.c_void_p, _c_i64p, _c_i64p]),
     "npb_measure_fp64_peak": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),
     "npb_measure_copy_bw": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_double)]),
     "npb_flush_l2": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64]),
@@ -241,6 +242,12 @@ class Context:
         v = ctypes.c_int64(0)
         check(self.lib.npb_launch_count(self.handle, ctypes.byref(v)))
         return int(v.value)
+
+    def check_guards(self):
+        """(guarded blocks, damaged blocks) — both 0 unless NPB_DEBUG_GUARDS=1 was set before the library's first use."""
+        nb, nd = ctypes.c_int64(0), ctypes.c_int64(0)
+        check(self.lib.npb_check_guards(self.handle, ctypes.byref(nb), ctypes.byref(nd)))
+        return int(nb.value), int(nd.value)
 
     def measure_fp64_peak(self):
         v = ctypes.c_double(0.0)

@@ -28,6 +28,55 @@ extern "C" int npb_device_count(int *count)
     return NPB_OK;
 }
 
+// ---- guard words (debug aid; compute-sanitizer is not available on the pool) ----
+// With NPB_DEBUG_GUARDS=1 every device block handed out by npb_alloc / npb_ensure is followed by 64 bytes of a known
+// pattern; npb_check_guards reads them back.  A kernel that writes past the end of its buffer (the likeliest kind
+// of bad access in the scatter / emit kernels) shows up in the GPU tests instead of corrupting a neighbour silently.
+#include <map>
+#include <mutex>
+#define NPB_GUARD_BYTES 64
+#define NPB_GUARD_BYTE 0xA5
+static std::mutex g_guard_mu;
+static std::map<void *, size_t> g_guard;   // block -> offset of its guard
+static bool guards_on()
+{
+    static const bool on = [] { const char *e = getenv("NPB_DEBUG_GUARDS"); return e && e[0] == '1'; }();
+    return on;
+}
+static int guard_arm(void *p, size_t offset)
+{
+    NPB_CUDA(cudaMemset((char *)p + offset, NPB_GUARD_BYTE, NPB_GUARD_BYTES));
+    std::lock_guard<std::mutex> lk(g_guard_mu);
+    g_guard[p] = offset;
+    return NPB_OK;
+}
+void npb_guard_forget(void *p)
+{
+    if (!p || !guards_on()) return;
+    std::lock_guard<std::mutex> lk(g_guard_mu);
+    g_guard.erase(p);
+}
+extern "C" int npb_check_guards(npb_ctx *c, int64_t *n_blocks, int64_t *n_damaged)
+{
+    if (!c || !n_blocks || !n_damaged) return NPB_ERR_ARG;
+    *n_blocks = *n_damaged = 0;
+    if (!guards_on()) return NPB_OK;
+    NPB_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(g_guard_mu);
+    unsigned char h[NPB_GUARD_BYTES];
+    for (auto &kv : g_guard) {
+        NPB_CUDA(cudaMemcpy(h, (char *)kv.first + kv.second, NPB_GUARD_BYTES, cudaMemcpyDeviceToHost));
+        bool ok = true;
+        for (int i = 0; i < NPB_GUARD_BYTES; i++) ok = ok && h[i] == NPB_GUARD_BYTE;
+        (*n_blocks)++;
+        if (!ok) {
+            (*n_damaged)++;
+            npb_set_error("guard after device block %p (+%zu bytes) was overwritten", kv.first, kv.second);
+        }
+    }
+    return NPB_OK;
+}
+
 int npb_alloc(npb_ctx *c, void **p, size_t bytes, bool owned_by_mesh)
 {
     *p = nullptr;
@@ -35,15 +84,24 @@ int npb_alloc(npb_ctx *c, void **p, size_t bytes, bool owned_by_mesh)
     // (k2_tile_pipe.cu) and may read up to 15 bytes past the last element
     NPB_CUDA(cudaMalloc(p, bytes + 64));
     if (owned_by_mesh) c->owned.push_back(*p);
+    if (guards_on()) NPB_TRY(guard_arm(*p, bytes));
     return NPB_OK;
 }
 
 int npb_ensure(void **p, size_t *cap, size_t bytes)
 {
     if (*p && *cap >= bytes) return NPB_OK;
-    if (*p) NPB_CUDA(cudaFree(*p));
+    if (*p) {
+        npb_guard_forget(*p);
+        NPB_CUDA(cudaFree(*p));
+    }
     *p = nullptr;
     *cap = 0;
+    if (guards_on()) {   // exact size + guard: the next larger request reallocates, so the guard follows the largest one
+        NPB_CUDA(cudaMalloc(p, bytes + NPB_GUARD_BYTES));
+        *cap = bytes;
+        return guard_arm(*p, bytes);
+    }
     size_t want = bytes + bytes / 8 + 256;
     NPB_CUDA(cudaMalloc(p, want));
     *cap = want;
@@ -217,7 +275,10 @@ int npb_psup_stats(npb_ctx *c);
 
 static void free_mesh(npb_ctx *c)
 {
-    for (void *p : c->owned) cudaFree(p);
+    for (void *p : c->owned) {
+        npb_guard_forget(p);
+        cudaFree(p);
+    }
     c->owned.clear();
     c->inpoel = c->esup_ptr = c->esup = c->esuel = c->infael = c->inpofa = c->fsup_ptr = c->fsup = nullptr;
     c->psup_ptr = c->psup = c->node_list = nullptr;
@@ -292,13 +353,13 @@ extern "C" int npb_destroy(npb_ctx *c)
     npb_resolve_timers(c);
     npb_comm_destroy(c);
     free_mesh(c);
-    if (c->wbuf) cudaFree(c->wbuf);
-    if (c->indices) cudaFree(c->indices);
-    if (c->data) cudaFree(c->data);
-    if (c->scratch) cudaFree(c->scratch);
-    if (c->scan_tmp) cudaFree(c->scan_tmp);
-    if (c->part_tmp) cudaFree(c->part_tmp);
-    if (c->gls_ws) cudaFree(c->gls_ws);
+    if (c->wbuf) { npb_guard_forget(c->wbuf); cudaFree(c->wbuf); }
+    if (c->indices) { npb_guard_forget(c->indices); cudaFree(c->indices); }
+    if (c->data) { npb_guard_forget(c->data); cudaFree(c->data); }
+    if (c->scratch) { npb_guard_forget(c->scratch); cudaFree(c->scratch); }
+    if (c->scan_tmp) { npb_guard_forget(c->scan_tmp); cudaFree(c->scan_tmp); }
+    if (c->part_tmp) { npb_guard_forget(c->part_tmp); cudaFree(c->part_tmp); }
+    if (c->gls_ws) { npb_guard_forget(c->gls_ws); cudaFree(c->gls_ws); }
     if (c->counters) cudaFree(c->counters);
     if (c->h_small) cudaFreeHost(c->h_small);
     for (int i = 0; i < 2; i++) {
@@ -826,15 +887,25 @@ int npb_ensure_out(npb_ctx *c, size_t n)
 {
     size_t n1 = n > 0 ? n : 1;
     if (c->out_cap >= n1) return NPB_OK;
-    if (c->indices) NPB_CUDA(cudaFree(c->indices));
-    if (c->data) NPB_CUDA(cudaFree(c->data));
+    if (c->indices) {
+        npb_guard_forget(c->indices);
+        NPB_CUDA(cudaFree(c->indices));
+    }
+    if (c->data) {
+        npb_guard_forget(c->data);
+        NPB_CUDA(cudaFree(c->data));
+    }
     c->indices = nullptr;
     c->data = nullptr;
     c->out_cap = 0;
-    size_t want = n1 + n1 / 16 + 64;
-    NPB_CUDA(cudaMalloc(&c->indices, sizeof(int32_t) * want));
-    NPB_CUDA(cudaMalloc(&c->data, sizeof(double) * want));
+    size_t want = guards_on() ? n1 : n1 + n1 / 16 + 64;   // guard mode: exact capacity, guard right behind it
+    NPB_CUDA(cudaMalloc(&c->indices, sizeof(int32_t) * want + NPB_GUARD_BYTES));
+    NPB_CUDA(cudaMalloc(&c->data, sizeof(double) * want + NPB_GUARD_BYTES));
     c->out_cap = want;
+    if (guards_on()) {
+        NPB_TRY(guard_arm(c->indices, sizeof(int32_t) * want));
+        NPB_TRY(guard_arm(c->data, sizeof(double) * want));
+    }
     return NPB_OK;
 }
 

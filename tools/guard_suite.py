@@ -1,13 +1,18 @@
-"""Small-mesh pass over every kernel family, meant to run under compute-sanitizer (memcheck / racecheck / synccheck).
+"""Small-mesh pass over every kernel family with guard words behind every device block (NPB_DEBUG_GUARDS=1).
 
-usage: compute-sanitizer --tool memcheck --error-exitcode 1 python tools/sanitize_suite.py [quick]
+usage: python tools/guard_suite.py [quick]
 
-Each case is one load_mesh + idw / ls / gls through the default pipeline, the plain two-pass path and the plug-in
-(dense) entry point, plus the lazily built exports (psup, edges).  Alternative kernels are selected the way the tests
-select them (environment switches read at call time).  Prints one line per case; exits non-zero on a host-side error.
+compute-sanitizer is closed on the pool, so out-of-bounds WRITES are looked for this way: the library puts 64 known
+bytes behind every block it allocates and `npb_check_guards` reads them back after each case.  Each case is one
+load_mesh + idw / ls / gls through the default pipeline, the plain two-pass path and the plug-in (dense) entry point,
+plus the lazily built exports (psup, edges).  Alternative kernels are selected the way the tests select them
+(environment switches read at call time).  Prints one line per case; exits non-zero when a guard was overwritten.
+tests/test_gpu_guards.py runs it in a subprocess (the guard switch is read once per process).
 """
 import os
 import sys
+
+os.environ["NPB_DEBUG_GUARDS"] = "1"   # before the library's first use
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -25,7 +30,11 @@ def run(kind, n, label, env=None, ctor=None, methods=("idw", "ls", "gls"), expor
         os.environ[k] = v
     try:
         mesh = meshgen.make_case(kind, n, **kw)
-        I = ninpol_b200.Interpolator(build_edges=exports, **(ctor or {}))
+        ctor = dict(ctor or {})
+        min_chunk = ctor.pop("min_chunk_nodes", None)
+        I = ninpol_b200.Interpolator(build_edges=exports, **ctor)
+        if min_chunk is not None:
+            I.min_chunk_nodes = min_chunk
         I.load_mesh(mesh_obj=mesh)
         out = []
         for m in methods:
@@ -36,7 +45,12 @@ def run(kind, n, label, env=None, ctor=None, methods=("idw", "ls", "gls"), expor
             out.append(("psup", int(np.asarray(g.psup).size), 0.0))
             out.append(("inpoed", int(np.asarray(g.inpoed).shape[0]), 0.0))
             out.append(("esuf", int(np.asarray(g.esuf).size), 0.0))
-        print(label, kind, n, out, flush=True)
+        blocks, damaged = I._ctx.check_guards()
+        print(label, kind, n, out, "guards", blocks, "damaged", damaged, flush=True)
+        if blocks == 0:
+            raise SystemExit("guards are off: NPB_DEBUG_GUARDS was not seen by the library")
+        if damaged:
+            raise SystemExit(f"{label} {kind} {n}: {damaged} guard(s) overwritten: {ninpol_b200._capi.load_library().npb_last_error().decode()}")
         del I
     finally:
         for k, v in saved.items():
@@ -56,7 +70,10 @@ def plugin(kind, n):
         neumann = np.zeros(g.n_points)
         I.supported_methods[m](g, I.cells_data, I.points_data, I.faces_data, I.variable_to_index, "u",
                                np.arange(g.n_points), weights, neumann)
-        print("plugin", kind, n, m, float(np.nansum(weights)), flush=True)
+        blocks, damaged = I._ctx.check_guards()
+        print("plugin", kind, n, m, float(np.nansum(weights)), "guards", blocks, "damaged", damaged, flush=True)
+        if damaged:
+            raise SystemExit(f"plugin {m}: {damaged} guard(s) overwritten")
 
 
 n3 = 4 if QUICK else 6
@@ -79,4 +96,4 @@ for v in ("0", "1", "2", "3"):
     run("hex", n3, "tile-variant-" + v, env={"NPB_TILE_VARIANT": v}, methods=("idw", "ls"))
 run("hex", n3, "no-neumann", neumann_rate=0.0)
 plugin("tet", n3)
-print("sanitize suite done", flush=True)
+print("guard suite done", flush=True)
