@@ -468,7 +468,8 @@ def run_ours(args, rank, world):
            "ms_per_step": e2e_s * 1e3,
            "api": (f"Interpolator({'comm=comm, gather=' + repr(e2e_gather) if world > 1 else ''}).interpolate(variable, method) after "
                    "invalidate_inputs() - the constructor's defaults: page-locked pooled outputs, inputs page-locked in place, 8 node chunks. "
-                   "Per step: H2D of the flags and (GLS) of the permeability / diff_mag slices this rank's nodes read, kernels, D2H of the CSR; "
+                   "Per step: H2D of the flags (N > 1: of the slice of this rank's nodes; the ranks sum the slice checksums to learn that the resident row is unchanged) "
+                   "and (GLS) of the permeability / diff_mag slices this rank's nodes read, kernels, D2H of the CSR; "
                    "uploads, kernels and downloads overlap chunk by chunk on separate streams. gather='host': every rank writes its rows into "
                    "one page-locked host mapping shared by the ranks (all PCIe links in parallel), one NCCL 1-int exchange closes the step; "
                    "gather='all': row blocks all-gathered over NCCL / NVLink, every rank downloads the whole CSR. Byte counts are sums over ranks.")}

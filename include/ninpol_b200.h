@@ -123,6 +123,11 @@ int npb_set_point_flags(npb_ctx *ctx, const int64_t *neumann_flag, int64_t n_poi
 /* Same, from the float64 point-data row itself: the `.astype(int)` truncation (NaN / inf -> non-zero, as
  * numpy casts them) happens on the device, which saves the host a pass over the array. */
 int npb_set_point_flags_f64(npb_ctx *ctx, const double *neumann_flag, int64_t n_points);
+/* Multi-GPU re-staging of a flag row that is expected to be unchanged (no reference counterpart): the rank uploads only
+ * the slice [first, first + count) it owns; the slices of all ranks must tile [0, n_points).  *checksum = the checksum of
+ * the whole row, summed over the ranks (collective: one 8-byte ncclAllReduce), in the form of the "flags_checksum" scalar.
+ * Equal to the resident row's checksum: nothing else needs to move.  Different: call npb_set_point_flags_f64. */
+int npb_set_point_flags_f64_range(npb_ctx *ctx, const double *flag_slice, int64_t first, int64_t count, int64_t *checksum);
 
 /* K2 + K3 (+ K4) — weights and CSR.
  * Replaces: Interpolator.prepare_interpolator -> XInterpolation.prepare (interpolator.pyx:631-670;

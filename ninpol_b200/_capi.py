@@ -36,6 +36,7 @@ _SIGNATURES = {
     "npb_set_cell_field": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64]),
     "npb_set_point_flags": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]),
     "npb_set_point_flags_f64": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]),
+    "npb_set_point_flags_f64_range": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, _c_i64p]),
     "npb_interpolate_count": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_i64p]),
     "npb_interpolate_fetch": (ctypes.c_int, [ctypes.c_void_p] * 5),
     "npb_interpolate_dense": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
@@ -190,6 +191,15 @@ class Context:
             return
         f = np.ascontiguousarray(flags, dtype=np.int64)
         check(self.lib.npb_set_point_flags(self.handle, _ptr(f), f.size))
+
+    def set_point_flags_slice(self, flags, first, count):
+        """Collective: upload flags[first:first + count] only (float64, contiguous); returns the checksum of the whole
+        row summed over the ranks.  Equal to scalar('flags_checksum'): the resident row is still right."""
+        part = flags[first:first + count]
+        v = ctypes.c_int64(0)
+        check(self.lib.npb_set_point_flags_f64_range(self.handle, _ptr(part) if count > 0 else None, int(first), int(count),
+                                                     ctypes.byref(v)))
+        return int(v.value)
 
     # --- K2 / K3 / K4 ---
     def interpolate_run(self, method, n_chunks, perm=None, diff_mag=None, indptr=None, indices=None, data=None, neumann=None):

@@ -294,6 +294,9 @@ static void free_mesh(npb_ctx *c)
     c->counted = false;
     c->plan_kind = 0;
     c->plan_chunks = 0;
+    c->chunk_node.clear();
+    c->chunk_efirst.clear();
+    c->chunk_elast.clear();
     c->plan_failed[0] = c->plan_failed[1] = c->plan_failed[2] = false;
 }
 
@@ -689,13 +692,20 @@ extern "C" int npb_set_cell_field_range(npb_ctx *c, const char *name, const doub
     return NPB_OK;
 }
 
-// Both flag kernels also fold WHICH nodes are flagged into a 64-bit checksum (sum of (i + 1) * golden-ratio constant over
-// the flagged nodes, wrapping): the host re-cuts the node partition only when it changes, without a pass over the array.
+// Both flag kernels also fold WHICH nodes are flagged into a 64-bit checksum: the wrapping sum, over the flagged nodes, of
+// a mixed (splitmix64) image of the node id.  The host re-cuts the node partition only when it changes, without a pass
+// over the array; being a sum, it can be formed slice by slice on different ranks (npb_set_point_flags_f64_range).
 #define NPB_FLAG_MIX 0x9E3779B97F4A7C15ull
 static int read_flag_checksum(npb_ctx *c);
 __device__ __forceinline__ void flag_checksum(bool set, i64 i, unsigned long long *sum)
 {
-    unsigned long long v = set ? (unsigned long long)(i + 1) * NPB_FLAG_MIX : 0ull;
+    unsigned long long v = 0ull;
+    if (set) {
+        v = (unsigned long long)(i + 1) * NPB_FLAG_MIX;
+        v ^= v >> 30; v *= 0xBF58476D1CE4E5B9ull;
+        v ^= v >> 27; v *= 0x94D049BB133111EBull;
+        v ^= v >> 31;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(sum, v);
@@ -741,17 +751,18 @@ extern "C" int npb_set_point_flags(npb_ctx *c, const int64_t *flag, int64_t n_po
     return NPB_OK;
 }
 
-__global__ void k_flags_f64(const double *__restrict__ in, i64 n, uint8_t *__restrict__ out, unsigned long long *__restrict__ sum)
+__global__ void k_flags_f64(const double *__restrict__ in, i64 first, i64 n, uint8_t *__restrict__ out,
+                            unsigned long long *__restrict__ sum)
 {
-    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;   // local index: in[i] is node first + i
     bool set = false;
     if (i < n) {
         double f = in[i];
         // numpy's float64 -> int64 cast truncates toward zero; NaN / inf become INT64_MIN (non-zero)
         set = (f != f || (long long)f != 0);
-        out[i] = set ? 1 : 0;
+        out[first + i] = set ? 1 : 0;
     }
-    flag_checksum(set, i, sum);
+    flag_checksum(set, first + i, sum);
 }
 
 static int read_flag_checksum(npb_ctx *c)
@@ -778,7 +789,7 @@ extern "C" int npb_set_point_flags_f64(npb_ctx *c, const double *flag, int64_t n
     NPB_TRY(npb_ensure(&c->scratch, &c->scratch_cap, sizeof(double) * (size_t)n_points));
     NPB_TRY(npb_h2d(c, c->scratch, flag, sizeof(double) * n_points));
     NPB_CUDA(cudaMemsetAsync(c->counters + 66, 0, sizeof(unsigned long long), c->stream));
-    k_flags_f64<<<npb_blocks(n_points, 256), 256, 0, c->stream>>>((const double *)c->scratch, n_points, c->nflag,
+    k_flags_f64<<<npb_blocks(n_points, 256), 256, 0, c->stream>>>((const double *)c->scratch, 0, n_points, c->nflag,
                                                                   (unsigned long long *)(c->counters + 66));
     NPB_LAUNCH(c);
     NPB_TRY(read_flag_checksum(c));
@@ -787,6 +798,46 @@ extern "C" int npb_set_point_flags_f64(npb_ctx *c, const double *flag, int64_t n
     c->plan_kind = 0;     // row lengths depend on the flags
     c->plan_failed[0] = c->plan_failed[1] = c->plan_failed[2] = false;
     c->fused_failed[0] = c->fused_failed[1] = false;
+    return NPB_OK;
+}
+
+int npb_k4_allreduce_u64(npb_ctx *c, unsigned long long *d_value);
+
+// Multi-GPU re-staging of flags that are expected to be unchanged: this rank uploads only the slice [first, first + count)
+// of the float64 flag row (the nodes it owns), the ranks add up the checksums of their slices, and *checksum is that
+// total in the form of the "flags_checksum" scalar.  When it equals the checksum of the flags already resident, the
+// other slices on this device are still right and nothing else needs to move (the row plan stays valid); otherwise the
+// caller uploads the whole row with npb_set_point_flags_f64.  The slices of the ranks must tile [0, n_points).
+extern "C" int npb_set_point_flags_f64_range(npb_ctx *c, const double *flag_slice, int64_t first, int64_t count, int64_t *checksum)
+{
+    if (!c || !checksum || (count > 0 && !flag_slice)) return NPB_ERR_ARG;
+    if (!c->mesh_loaded || !c->have_flags) {
+        npb_set_error("npb_set_point_flags_f64_range: a full flag row must have been set for this mesh first");
+        return NPB_ERR_STATE;
+    }
+    if (first < 0 || count < 0 || first + count > c->n_points) {
+        npb_set_error("npb_set_point_flags_f64_range: slice [%lld, %lld) outside [0, %lld)", (long long)first,
+                      (long long)(first + count), (long long)c->n_points);
+        return NPB_ERR_ARG;
+    }
+    NPB_CUDA(cudaSetDevice(c->device));
+    unsigned long long *sum = (unsigned long long *)(c->counters + 66);
+    NPB_CUDA(cudaMemsetAsync(sum, 0, sizeof(unsigned long long), c->stream));
+    if (count > 0) {
+        NPB_TRY(npb_ensure(&c->scratch, &c->scratch_cap, sizeof(double) * (size_t)count));
+        NPB_TRY(npb_h2d(c, c->scratch, flag_slice, sizeof(double) * (size_t)count));
+        k_flags_f64<<<npb_blocks(count, 256), 256, 0, c->stream>>>((const double *)c->scratch, first, count, c->nflag, sum);
+        NPB_LAUNCH(c);
+    }
+    if (c->world > 1) NPB_TRY(npb_k4_allreduce_u64(c, sum));
+    unsigned long long h = 0;
+    NPB_CUDA(cudaMemcpyAsync(&h, sum, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    NPB_CUDA(cudaStreamSynchronize(c->stream));
+    *checksum = (i64)(h >> 1);
+    if (*checksum != c->flags_checksum) {   // the flags changed somewhere: this device's copy is no longer trustworthy
+        c->counted = false;
+        c->plan_kind = 0;
+    }
     return NPB_OK;
 }
 

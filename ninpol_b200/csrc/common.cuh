@@ -146,6 +146,7 @@ struct npb_ctx {
     i64 plan_nnz = 0;
     int plan_chunks = 0;                 // chunk table below is valid for this many chunks per rank
     std::vector<i64> chunk_node, chunk_nz;   // [world * K + 1] node / nnz boundaries of every rank's chunks
+    std::vector<i64> chunk_efirst, chunk_elast;   // [K] element range this rank's chunk k reads (empty: not computed yet)
     bool gathered = false;               // indices / data / neumann of ALL ranks are on this device (gather = all)
 };
 

@@ -228,6 +228,17 @@ __device__ __forceinline__ void mf_store_cb(const double *src, int sld, int rows
 }
 
 #define MF_RPL 3   // front rows per lane in the panel factorisation: fronts of up to 96 rows
+#ifndef MF_APPLY_UNROLL
+#define MF_APPLY_UNROLL 4
+#endif
+#define MF_PRAGMA_(x) _Pragma(#x)
+#define MF_PRAGMA(x) MF_PRAGMA_(x)
+#define MF_UNROLL_APPLY MF_PRAGMA(unroll MF_APPLY_UNROLL)
+#ifdef MF_HH_NOINLINE
+#define MF_HH_INLINE __noinline__
+#else
+#define MF_HH_INLINE __forceinline__
+#endif
 
 // Householder scalars of one column: alpha = -sign(x0) |x|, beta = 2 / |v|^2 with v = x - alpha e1, and
 // rinv = 1 / alpha (kept on the diagonal of R for the back substitution).  sqrt and 1/alpha come from one
@@ -245,7 +256,7 @@ __device__ __forceinline__ double rcp_seed(double x)
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     return y;
 }
-__device__ __forceinline__ void hh_scalars(double sigma, double x0, double &alpha, double &beta, double &rinv)
+__device__ MF_HH_INLINE void hh_scalars(double sigma, double x0, double &alpha, double &beta, double &rinv)
 {
     if (sigma == 0.0) {   // zero column: identity reflector, zero pivot (NaN takes the normal path and propagates)
         alpha = 0.0;
@@ -740,10 +751,23 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
         ch_rows = 0;
         int npiv = 0;
         double fri0 = 0.0, fri1 = 0.0, fri2 = 0.0;   // 1 / alpha of the last chunk's pivots
+#ifdef MF_ZERO_FIRST
+        int rho_left = rho;   // rows of the S list not assembled yet
+#else
         (void)rho;
+#endif
         for (bool last = false; !last;) {
             // (d) assemble one chunk: lanes over front columns [pivot block | other blocks ascending | rhs]
             int rho_c = carry;
+#ifdef MF_ZERO_FIRST
+            {   // the rows this chunk assembles are cleared at once; the groups then copy only the entries they have
+                const int fill = min(rcap - carry, rho_left) * ld;
+                rho_left -= min(rcap - carry, rho_left);
+                double *z = Fm + carry * ld;
+                for (int i = lane; i < fill; i += 32) z[i] = 0.0;
+                __syncwarp();
+            }
+#endif
             while (t_next < nS && rho_c < rcap) {
                 const int g = w.s_list[t_next] & 0xffff;
                 const u64 mk = w.g_mask[g];
@@ -768,13 +792,16 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
                             src += Ga * gld;
                             ds += (unsigned)(Ga * ld * 8);
                         }
-                    } else {
+                    }
+#ifndef MF_ZERO_FIRST
+                    else {
                         double *dst = Fm + (rho_c + r0) * ld + j;
                         for (int r = r0; r < take; r += Ga) {
                             *dst = 0.0;
                             dst += Ga * ld;
                         }
                     }
+#endif
                 }
                 rho_c += take;
                 r_done += take;
@@ -878,7 +905,7 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
                 double wa = 0.0, wb = 0.0, wc = 0.0;
                 {
                     const double *vp = Fm + grp * ld;
-#pragma unroll 4
+MF_UNROLL_APPLY
                     for (int r = grp; r < rho_c; r += G) {
                         double f = vp[j];
                         double2 va = *reinterpret_cast<const double2 *>(vp + po);
@@ -899,7 +926,7 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
                 const double ca = par ? s1 : s0, cb = par ? s2 : s1, cc = par ? s0 : s2;
                 if (act) {
                     double *vp = Fm + grp * ld;
-#pragma unroll 4
+MF_UNROLL_APPLY
                     for (int r = grp; r < rho_c; r += G) {
                         double2 va = *reinterpret_cast<const double2 *>(vp + po);
                         double vc = vp[so];
@@ -915,7 +942,7 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
                 {
                     const double *fp = Fm + j;
                     const double *vp = Fm;
-#pragma unroll 4
+MF_UNROLL_APPLY
                     for (int r = 0; r < rho_c; r++) {
                         double f = *fp;
                         double2 va = *reinterpret_cast<const double2 *>(vp + po);
@@ -932,7 +959,7 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
                 {
                     double *fp = Fm + j;
                     const double *vp = Fm;
-#pragma unroll 4
+MF_UNROLL_APPLY
                     for (int r = 0; r < rho_c; r++) {
                         double2 va = *reinterpret_cast<const double2 *>(vp + po);
                         double vc = vp[so];

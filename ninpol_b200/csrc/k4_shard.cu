@@ -219,6 +219,15 @@ int npb_k4_share_flags(npb_ctx *c, const int *d_bad2, int host_flag, int *any)
     return NPB_OK;
 }
 
+// wrapping 64-bit sum over the ranks, in place, on the compute stream (the flag-slice checksums of capi.cu)
+int npb_k4_allreduce_u64(npb_ctx *c, unsigned long long *d_value)
+{
+    if (c->world == 1) return NPB_OK;
+    NcclApi *api = c->nccl;
+    NPB_NCCL(api->AllReduce(d_value, d_value, 1, ncclUint64, ncclSum, (ncclComm_t)c->comm, c->stream));
+    return NPB_OK;
+}
+
 // One chunk step of the pipelined all-gather-v: rank r owns nodes [node_lo[r], node_hi[r]) = CSR entries
 // [nz_lo[r], nz_hi[r]); every rank receives every block at its final position (one group of ncclSend / ncclRecv on `st`).
 int npb_k4_bcast_chunk(npb_ctx *c, cudaStream_t st, const std::vector<i64> &node_lo, const std::vector<i64> &node_hi,

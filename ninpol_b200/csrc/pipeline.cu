@@ -101,6 +101,7 @@ static int ensure_chunk_table(npb_ctx *c, int K)
 {
     if (c->plan_chunks == K && (int)c->chunk_node.size() == c->world * K + 1) return NPB_OK;
     const int W = c->world;
+    const std::vector<i64> old_nodes = c->chunk_node;
     c->chunk_node.assign((size_t)W * K + 1, 0);
     // Chunk sizes ramp up and down (weights 1, 2, 3, 3, ..., 3, 2): the upload of the first chunk and the download of
     // the last one are the two legs nothing can hide, so those chunks are the small ones.  Same rule on every rank.
@@ -114,6 +115,10 @@ static int ensure_chunk_table(npb_ctx *c, int K)
         for (int k = 0; k < K; k++) c->chunk_node[(size_t)r * K + k] = a + (n * cum[k]) / cum[K];
     }
     c->chunk_node[(size_t)W * K] = c->n_points;
+    if (c->chunk_node != old_nodes) {   // the element ranges of the chunks follow the node boundaries, not the plan
+        c->chunk_efirst.clear();
+        c->chunk_elast.clear();
+    }
     // one gather kernel would do; the table is tiny (W*K+1 <= 16*64+1) and read once per plan
     std::vector<int32_t> off((size_t)W * K + 1);
     for (size_t i = 0; i < off.size(); i++)
@@ -167,8 +172,8 @@ static int run_pipeline(npb_ctx *c, int method, int K, const double *perm_host, 
 
     const i64 *cn = c->chunk_node.data() + (size_t)R * K;   // this rank's chunk boundaries (K+1 entries)
     // element range each of this rank's chunks reads (GLS uploads)
-    std::vector<i64> e_first(K, 0), e_last(K, -1);
-    if (upload) {
+    if (upload && (int)c->chunk_efirst.size() != K) {   // a property of the chunk table: computed once per table
+        std::vector<i64> e_first(K, 0), e_last(K, -1);
         std::vector<int32_t> ptr(K + 1);
         for (int k = 0; k <= K; k++)
             NPB_CUDA(cudaMemcpyAsync(&ptr[k], c->esup_ptr + cn[k], sizeof(int32_t), cudaMemcpyDeviceToHost, s));
@@ -179,6 +184,11 @@ static int run_pipeline(npb_ctx *c, int method, int K, const double *perm_host, 
             e_first[k] = mn;
             e_last[k] = mx;
         }
+        c->chunk_efirst = e_first;
+        c->chunk_elast = e_last;
+    }
+    const std::vector<i64> &e_first = c->chunk_efirst, &e_last = c->chunk_elast;
+    if (upload) {
         if (!c->perm) NPB_TRY(npb_alloc(c, (void **)&c->perm, sizeof(double) * 9 * (size_t)c->n_elems));
         if (!c->diff_mag) NPB_TRY(npb_alloc(c, (void **)&c->diff_mag, sizeof(double) * (size_t)c->n_elems));
         c->have_perm = c->have_dm = false;   // until the last slice has landed

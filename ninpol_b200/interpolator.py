@@ -524,10 +524,20 @@ class Interpolator:
             flags = self._maybe_pin("neumann_flag", flags)     # truncated like .astype(int) on the device
         else:
             flags = flags.astype(DTYPE_I)
-        self._ctx.set_point_flags(flags)
+        h2d = None
+        if (self.comm.world > 1 and flags.dtype == DTYPE_F and self._flag_mask is not None
+                and self._partition_key == (method == "gls", self._flag_version, self._mesh_serial)):
+            # a flag row is resident and the node ranges cut for it are current: upload only the slice of the nodes this
+            # rank owns; the ranks add up the checksums of their slices.  Equal to the resident row's: it IS the resident
+            # row, and the partition, the row plan and the other ranks' slices on this device all stand.
+            lo, hi = int(self.partition_bounds[self.comm.rank]), int(self.partition_bounds[self.comm.rank + 1])
+            if (self._ctx.set_point_flags_slice(flags, lo, hi - lo), int(flags.shape[0])) == self._flag_mask:
+                h2d = (hi - lo) * flags.itemsize
+        if h2d is None:
+            self._ctx.set_point_flags(flags)
+            h2d = flags.nbytes
         self._flags_host = flags
-        h2d = flags.nbytes
-        if self.comm.world > 1:
+        if self.comm.world > 1 and h2d == flags.nbytes:
             # the node ranges depend on WHICH nodes are flagged (skipped nodes cost nothing): re-cut them only when that
             # set changed - cutting is a few numpy passes over all nodes, 150 ms at 8.5M nodes.  The flag kernel folds
             # the set into a 64-bit checksum on the device, so the test costs no pass over the array either.

@@ -60,4 +60,43 @@ for kind, n, kw in CASES:
             print(f"rank {comm.rank}/{comm.world} {kind}{n}{'s' if kw.get('scramble') else ''} gather={gather} chunks={chunks} {method}: "
                   f"{'OK' if good else 'MISMATCH'} nnz {W.nnz} rows [{lo},{hi}) bounds {bounds}", flush=True)
             ok = ok and good
+    # ---- flags re-staged slice by slice (npb_set_point_flags_f64_range) ----
+    # unchanged row: only this rank's slice is uploaded; a row changed anywhere is caught by the summed checksum, the
+    # whole row is uploaded again and the node ranges are cut anew
+    I.set_gather("all")
+    I.stream_chunks = 8
+    for method in ("idw", "gls"):
+        I.invalidate_inputs()
+        I.interpolate("u", method)
+        I.invalidate_inputs()
+        W, nv = I.interpolate("u", method)
+        b = [int(x) for x in I.partition_bounds]
+        flag_bytes = 8 * (b[comm.rank + 1] - b[comm.rank])
+        moved = I.last_timings["h2d_input_bytes"] - (80 * max(0, I._elem_range[1] - I._elem_range[0] + 1) if method == "gls" else 0)
+        Wo, nvo = ref[method]
+        good = moved == flag_bytes and np.array_equal(W.indptr, Wo.indptr) and np.array_equal(W.indices, Wo.indices)
+        print(f"rank {comm.rank}/{comm.world} {kind}{n} flag slice, unchanged row, {method}: {'OK' if good else 'MISMATCH'} "
+              f"(flag bytes moved {moved}, slice {flag_bytes}, row {8 * W.shape[0]})", flush=True)
+        ok = ok and good
+    name = "neumann_flag_u"
+    flag = np.array(mesh.point_data[name])
+    p = mesh.points
+    live = p.max(axis=0) > p.min(axis=0)
+    hull = np.any(((p == p.min(axis=0)) | (p == p.max(axis=0))) & live[None, :], axis=1)
+    idx = np.flatnonzero(hull)
+    flip = np.concatenate([idx[:3], idx[-3:]])          # nodes of the first and of the last rank
+    flag[flip] = 1.0 - flag[flip]
+    mesh.point_data[name] = flag
+    I.load_point_data()
+    O2 = oracle.OracleInterpolator().load_mesh(mesh, build_psup=False)
+    for method in ("idw", "gls"):
+        W, nv = I.interpolate("u", method)
+        Wo, nvo = O2.interpolate("u", method)
+        good = np.array_equal(W.indptr, Wo.indptr) and np.array_equal(W.indices, Wo.indices)
+        if method == "idw":
+            good = good and np.array_equal(W.data, Wo.data, equal_nan=True) and np.array_equal(nv, nvo)
+        else:
+            good = good and np.allclose(W.data, Wo.data, rtol=0, atol=1e-11) and np.allclose(nv, nvo, rtol=0, atol=1e-11)
+        print(f"rank {comm.rank}/{comm.world} {kind}{n} flag slice, CHANGED row, {method}: {'OK' if good else 'MISMATCH'} nnz {W.nnz}", flush=True)
+        ok = ok and good
 sys.exit(0 if ok else 1)

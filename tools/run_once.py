@@ -14,6 +14,6 @@ I.load_mesh(mesh_obj=mesh)
 for meth in method.split(","):
     for _ in range(rep):
         W, nv = I.interpolate("u", meth)
-    print(kind, n, meth, "nnz", W.nnz, {k: round(v, 3) for k, v in I.last_timings.items()})
+    print(kind, n, meth, "nnz", W.nnz, "sum", repr(float(W.data.sum())), "neumann", repr(float(nv.sum())), {k: round(v, 3) for k, v in I.last_timings.items()})
 names = ["k2", "k2_main", "k2_gls_c1", "k2_gls_c2", "k2_gls_c3", "k2_gls_c4", "k2_gls_c5", "k2_gls_c6", "k2_gls_c7", "k2_gls_dense", "gls_dense_nodes"]
 print({n: round(I._ctx.timing_or(n, -1), 3) for n in names})
