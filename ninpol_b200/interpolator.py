@@ -167,6 +167,9 @@ class Interpolator:
         # (npb_interpolate_run); results are bit-identical to the plain count + fetch path (stream_chunks=0)
         self.stream_chunks = int(stream_chunks)
         self.min_chunk_nodes = 200_000     # chunks only pay when each is long next to the launch / copy latencies
+        # GLS uploads 80 B per cell and spends ~70 ns per node: its chunks pay from 50 k nodes on (2M-tet mesh: 27.9 ms in
+        # one piece, 25.2 ms in six; profiles/r02_e2e_probe.log), and at 8 GPUs the two PCIe legs nothing hides get shorter
+        self.min_chunk_nodes_gls = 50_000
         if self.comm.world > 1:
             self._ctx.comm_init(self.comm.unique_id, self.comm.rank, self.comm.world)
             self._ctx.set_gather(gather)
@@ -667,7 +670,8 @@ class Interpolator:
                       self._out("data", cap, np.float64), self._out("neumann", n_points, np.float64))
             pinned = self.pinned_outputs
         # every rank must cut the same number of chunks (the NCCL gather is chunked alike): the rule uses global sizes
-        chunks = max(1, min(self.stream_chunks, n_points // (max(1, self.min_chunk_nodes) * world)))
+        rule = min(self.min_chunk_nodes, self.min_chunk_nodes_gls) if method == "gls" else self.min_chunk_nodes
+        chunks = max(1, min(self.stream_chunks, n_points // (max(1, rule) * world)))
         if pinned:
             nnz, fell_back = ctx.interpolate_run(method, chunks, perm, dm, *arrays)
         else:                         # pageable outputs: device-resident run, then the staged copies of fetch
