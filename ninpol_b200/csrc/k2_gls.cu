@@ -71,36 +71,59 @@ __host__ __device__ __forceinline__ size_t mf_smem_bytes(const MfClass &k)
     return (b + 15) & ~(size_t)15;
 }
 
-// per node: Dirichlet / Q8 nodes are finished here (zero row); the others get a size class
-__global__ void k_gls_classify(GlsArgs a, i64 lo, i64 hi, uint8_t *__restrict__ cls, int force_dense)
+// per node: Dirichlet / Q8 nodes are finished here (zero row); the others get a size class.
+// sig[k] / sig[MF_NCLASS + k]: smallest / largest star signature (E << 8 | F) seen in class k — equal when all stars of
+// the class have the same size, which is when the team launch pays (npb_k2_gls).
+__global__ void k_gls_classify(GlsArgs a, i64 lo, i64 hi, uint8_t *__restrict__ cls, int force_dense, int *__restrict__ sig)
 {
+    __shared__ int smin[MF_NCLASS], smax[MF_NCLASS];
+    if (threadIdx.x < MF_NCLASS) {
+        smin[threadIdx.x] = 0x7fffffff;
+        smax[threadIdx.x] = 0;
+    }
+    __syncthreads();
     i64 p = lo + (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= hi) return;
-    int eb = a.esup_ptr[p], ee = a.esup_ptr[p + 1];
-    int fb = a.fsup_ptr[p], fe = a.fsup_ptr[p + 1];
-    int E = ee - eb, F = fe - fb;
-    bool neu = a.nflag[p] != 0;
-    int nb = 0;
-    bool skip = (a.bpoint[p] && !neu);  // gls.pyx:165-166
-    if (!skip) {
-        for (int q = fb; q < fe; q++) nb += (a.esuf2[a.fsup[q]].y < 0) ? 1 : 0;
-        if (nb >= F) skip = true;  // gls.pyx:266-267 + DGELS on a zero matrix -> zero weights (Q8)
-    }
-    if (skip) {
-        double *w = a.wbuf + ((i64)eb - a.wbase);
-        for (int k = 0; k < E; k++) w[k] = 0.0;
-        a.rowcnt[p] = 0;
-        a.neumann[p] = 0.0;
-        cls[p] = 0;
-        return;
-    }
-    int k = MF_NCLASS - 1;
-    for (int q = 1; q < MF_NCLASS - 1 && !force_dense; q++)
-        if (E <= c_mf[q].ecap && F <= c_mf[q].fcap_f) {
-            k = q;
-            break;
+    if (p < hi) {
+        int eb = a.esup_ptr[p], ee = a.esup_ptr[p + 1];
+        int fb = a.fsup_ptr[p], fe = a.fsup_ptr[p + 1];
+        int E = ee - eb, F = fe - fb;
+        bool neu = a.nflag[p] != 0;
+        int nb = 0;
+        bool skip = (a.bpoint[p] && !neu);  // gls.pyx:165-166
+        if (!skip) {
+            for (int q = fb; q < fe; q++) nb += (a.esuf2[a.fsup[q]].y < 0) ? 1 : 0;
+            if (nb >= F) skip = true;  // gls.pyx:266-267 + DGELS on a zero matrix -> zero weights (Q8)
         }
-    cls[p] = (uint8_t)k;
+        if (skip) {
+            double *w = a.wbuf + ((i64)eb - a.wbase);
+            for (int k = 0; k < E; k++) w[k] = 0.0;
+            a.rowcnt[p] = 0;
+            a.neumann[p] = 0.0;
+            cls[p] = 0;
+        } else {
+            int k = MF_NCLASS - 1;
+            for (int q = 1; q < MF_NCLASS - 1 && !force_dense; q++)
+                if (E <= c_mf[q].ecap && F <= c_mf[q].fcap_f) {
+                    k = q;
+                    break;
+                }
+            cls[p] = (uint8_t)k;
+            const int sg = (min(E, 0xffff) << 8) | min(F, 255);
+            atomicMin(&smin[k], sg);
+            atomicMax(&smax[k], sg);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < MF_NCLASS && smax[threadIdx.x] != 0) {
+        atomicMin(&sig[threadIdx.x], smin[threadIdx.x]);
+        atomicMax(&sig[MF_NCLASS + threadIdx.x], smax[threadIdx.x]);
+    }
+}
+
+// hands the signature ranges to the host through the mapped block (read after the partition's synchronisation)
+__global__ void k_gls_publish_sig(const int *__restrict__ sig, int *__restrict__ mapped)
+{
+    if (threadIdx.x < 2 * MF_NCLASS) mapped[threadIdx.x] = sig[threadIdx.x];
 }
 
 __device__ __forceinline__ u64 warp_or64(u64 v)
@@ -284,7 +307,18 @@ __device__ MF_HH_INLINE void hh_scalars(double sigma, double x0, double &alpha, 
 }
 
 // returns 0 on success, 1 when the star does not fit this class (caller reroutes it to the dense kernel)
-__device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfClass &kc, double *rslab, double *garena, int flags)
+// Team mode (experimental, k_gls_mf_team): the warps of one CTA keep loosely in step, front by front, so that they run
+// the same stretch of the 150 KB kernel body at the same time and share its instruction fetches.  No barrier: a warp
+// that is ahead of the slowest live warp by more than `slack` fronts naps for a bounded number of rounds.
+struct MfTeam {
+    volatile unsigned *prog;   // shared: fronts started so far, one counter per warp (0xffffffff: warp has left)
+    int warp, team, slack, spins;
+    unsigned step;
+};
+
+template <bool TEAM>
+__device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfClass &kc, double *rslab, double *garena, int flags,
+                       MfTeam *tm = nullptr)
 {
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
@@ -671,6 +705,17 @@ __device__ int mf_node(const GlsArgs &a, int p, unsigned char *smem, const MfCla
     int ch_rows = 0, ch_off = 0, ch_ld = 0;
     u64 ch_mask = 0;
     while (alive) {
+        if (TEAM) {
+            tm->step++;
+            if (lane == 0) tm->prog[tm->warp] = tm->step;
+            for (int spin = 0; spin < tm->spins; spin++) {
+                unsigned mn = 0xffffffffu;
+                if (lane < tm->team) mn = tm->prog[lane];
+                mn = __reduce_min_sync(FULL, mn);
+                if (tm->step <= mn + (unsigned)tm->slack) break;
+                __nanosleep(64);
+            }
+        }
         // (a) minimum-degree pivot block
         unsigned keyA = ((alive >> lane) & 1ull) ? (unsigned)((__popcll(adjA) << 8) | lane) : 0xffffffffu;
         unsigned keyB = ((alive >> (lane + 32)) & 1ull) ? (unsigned)((__popcll(adjB) << 8) | (lane + 32)) : 0xffffffffu;
@@ -1147,10 +1192,42 @@ k_gls_mf(GlsArgs a, const int32_t *__restrict__ list, int count, int *__restrict
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= count) break;
         int p = list[i];
-        int rc = mf_node(a, p, smem_mf, kc, rslab, garena, flags);
+        int rc = mf_node<false>(a, p, smem_mf, kc, rslab, garena, flags);
         __syncwarp();
         if (rc != 0 && threadIdx.x == 0) overflow[atomicAdd(n_overflow, 1)] = p;
     }
+}
+
+// Team launch: up to WARPS one-node warps per CTA (blockDim.x / 32 of them), one CTA per SM, loosely in step (see MfTeam).
+// WARPS only sets the register budget (12: 168 registers, 16: 128), like MINBLOCKS of k_gls_mf.
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, 1)
+k_gls_mf_team(GlsArgs a, const int32_t *__restrict__ list, int count, int *__restrict__ counter, int klass,
+              int32_t *__restrict__ overflow, int *__restrict__ n_overflow, double *__restrict__ slabs, int flags,
+              int smem_per_warp, int slack, int spins)
+{
+    extern __shared__ __align__(16) unsigned char smem_mf[];
+    const MfClass kc = c_mf[klass];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, team = blockDim.x >> 5;
+    MfTeam tm;
+    tm.prog = (volatile unsigned *)smem_mf;
+    tm.warp = warp; tm.team = team; tm.slack = slack; tm.spins = spins; tm.step = 0;
+    if (lane == 0) tm.prog[warp] = 0;
+    __syncthreads();
+    unsigned char *my = smem_mf + 128 + (size_t)warp * smem_per_warp;
+    double *rslab = slabs + ((size_t)blockIdx.x * team + warp) * kc.acap * 2;
+    double *garena = rslab + kc.acap;
+    while (true) {
+        int i = 0;
+        if (lane == 0) i = atomicAdd(counter, 1);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= count) break;
+        int p = list[i];
+        int rc = mf_node<true>(a, p, my, kc, rslab, garena, flags, &tm);
+        __syncwarp();
+        if (rc != 0 && lane == 0) overflow[atomicAdd(n_overflow, 1)] = p;
+    }
+    if (lane == 0) tm.prog[warp] = 0xffffffffu;   // the others no longer wait for this warp
 }
 
 int npb_k2_gls(npb_ctx *c, i64 lo, i64 hi)
@@ -1176,7 +1253,12 @@ int npb_k2_gls(npb_ctx *c, i64 lo, i64 hi)
     // 2-D meshes: every star is a small, nearly consistent system (weights up to +-150, residual << 1): all of them
     // take the dense kernel, which forms the residual through the reflectors (see k2_gls_dense.cu)
     const int force_dense = ((force && force[0] == '1') || c->dim == 2) ? 1 : 0;
-    k_gls_classify<<<npb_blocks(nloc, 256), 256, 0, s>>>(a, lo, hi, cls, force_dense);
+    int *sig = c->counters + 70;   // [2 * MF_NCLASS]: min / max star signature per class
+    NPB_CUDA(cudaMemsetAsync(sig, 0x7f, sizeof(int) * MF_NCLASS, s));
+    NPB_CUDA(cudaMemsetAsync(sig + MF_NCLASS, 0, sizeof(int) * MF_NCLASS, s));
+    k_gls_classify<<<npb_blocks(nloc, 256), 256, 0, s>>>(a, lo, hi, cls, force_dense, sig);
+    NPB_LAUNCH(c);
+    k_gls_publish_sig<<<1, 32, 0, s>>>(sig, c->d_small + 44);
     NPB_LAUNCH(c);
     {   // experiments: NPB_GLS_FCAP="class:doubles[,class:doubles...]" overrides the front sizes (re-read every pass)
         static const MfClass defaults[MF_NCLASS] = MF_CLASS_TABLE;
@@ -1236,6 +1318,35 @@ int npb_k2_gls(npb_ctx *c, i64 lo, i64 hi)
         k_gls_mf<V><<<grid, 32, smem, s>>>(a, list, count, counter, k, overflow, n_overflow, (double *)c->gls_ws, \
                                            mf_flags);                                                             \
     } while (0)
+        // Team launch (the warps of an SM in one CTA, loosely in step, so that they share instruction fetches): pays
+        // when the stars of the class are all alike - every node then runs the same instruction stream (structured
+        // tets: -9 %) - and costs when they differ (mixed mesh: +20 %), so it is taken for the 168-register classes
+        // whose smallest and largest star signature coincide.  NPB_GLS_TEAM = "off" | "slack[,spins]" overrides (tests, A/B).
+        const char *team = getenv("NPB_GLS_TEAM");
+        const bool uniform_stars = c->h_small[44 + k] == c->h_small[44 + MF_NCLASS + k];
+        bool team_on = variant == 12 && per_sm == 12 && uniform_stars && count >= 12 * 64;
+        int slack = 1, spins = 16;
+        if (team) {
+            team_on = strcmp(team, "off") != 0 && variant != 24 && per_sm >= 2 && per_sm <= 32;
+            slack = atoi(team);
+            const char *comma = strchr(team, ',');
+            if (comma) spins = atoi(comma + 1);
+        }
+        if (team_on) {
+            const int tsmem = 128 + per_sm * smem;
+            grid = c->sm_count;
+            if ((i64)grid * per_sm > count) grid = (count + per_sm - 1) / per_sm;
+            NPB_TRY(npb_ensure(&c->gls_ws, &c->gls_ws_cap, sizeof(double) * (size_t)grid * per_sm * h_mf[k].acap * 2));
+            if (variant == 16) {
+                NPB_CUDA(cudaFuncSetAttribute(k_gls_mf_team<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsmem));
+                k_gls_mf_team<16><<<grid, 32 * per_sm, tsmem, s>>>(a, list, count, counter, k, overflow, n_overflow,
+                                                                  (double *)c->gls_ws, mf_flags, smem, slack, spins);
+            } else {
+                NPB_CUDA(cudaFuncSetAttribute(k_gls_mf_team<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsmem));
+                k_gls_mf_team<12><<<grid, 32 * per_sm, tsmem, s>>>(a, list, count, counter, k, overflow, n_overflow,
+                                                                  (double *)c->gls_ws, mf_flags, smem, slack, spins);
+            }
+        } else
         if (variant == 24) MF_LAUNCH(24);
         else if (variant == 16) MF_LAUNCH(16);
         else MF_LAUNCH(12);

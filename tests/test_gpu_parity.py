@@ -181,6 +181,29 @@ def test_gls_general_fronts_only(kind, n, kw, monkeypatch):
     assert np.allclose(nv1, nv2, rtol=0, atol=1e-12)
 
 
+@pytest.mark.parametrize("kind,n,kw", [("tet", 12, {}), ("hex", 8, {}), ("mixed", 10, {"a": 2, "b": 5}), ("tet", 2, {})])
+@pytest.mark.parametrize("team", ["0,4", "1,16", "3,64"])
+def test_gls_team_launch_is_bit_identical(kind, n, kw, team, monkeypatch):
+    """NPB_GLS_TEAM forces the team launch (the warps of an SM in one CTA, loosely in step; taken by itself only for
+    classes of uniform stars) for every class: the per-node arithmetic is the same, so the result equals the one-warp
+    launch bit for bit - also with fewer nodes than warps in a team."""
+    import ninpol_b200
+    from ninpol_b200 import meshgen
+    monkeypatch.setenv("NPB_GLS_TEAM", "off")
+    I = ninpol_b200.Interpolator()
+    I.load_mesh(mesh_obj=meshgen.make_case(kind, n, **kw))
+    W1, nv1 = I.interpolate("u", "gls")
+    monkeypatch.setenv("NPB_GLS_TEAM", team)
+    J = ninpol_b200.Interpolator()
+    J.load_mesh(mesh_obj=meshgen.make_case(kind, n, **kw))
+    W2, nv2 = J.interpolate("u", "gls")
+    assert np.array_equal(W1.indptr, W2.indptr) and np.array_equal(W1.indices, W2.indices)
+    assert np.array_equal(W1.data, W2.data, equal_nan=True) and np.array_equal(nv1, nv2, equal_nan=True)
+    O = _pair(kind, n, kw)[1]
+    Wo, nvo = O.interpolate("u", "gls")
+    assert gls_errors(W2, Wo) <= GLS_TOL
+
+
 @pytest.mark.parametrize("kind,n,kw,chunks", [("tet", 9, {"scramble": True}, 4), ("mixed", 10, {"a": 2, "b": 5}, 7),
                                               ("hex", 8, {}, 3), ("tet", 12, {}, 64), ("tet", 1, {}, 8)])
 def test_streamed_pipeline_is_bit_identical(kind, n, kw, chunks):

@@ -89,6 +89,8 @@ run("tet", n3, "plain-esuel", env={"NPB_K1_ESUEL_PLAIN": "1"}, methods=("idw",))
 run("tet", n3, "simple-idw-ls", env={"NPB_FORCE_SIMPLE_IDW_LS": "1"}, methods=("idw", "ls"))
 run("tet", n3, "gls-dense", env={"NPB_FORCE_GLS_DENSE": "1"}, methods=("gls",))
 run("tet", n3, "gls-no-leaf", env={"NPB_GLS_NO_LEAF": "1"}, methods=("gls",))
+run("tet", n3 + 4, "gls-team", env={"NPB_GLS_TEAM": "1,16"}, methods=("gls",))
+run("mixed", n3 + 2, "gls-team", env={"NPB_GLS_TEAM": "0,4"}, methods=("gls",))
 run("mixed", n3 + 2, "gls-small-front", env={"NPB_GLS_FCAP": "512"}, methods=("gls",))
 for shape in ("A", "B", "C", "D"):
     run("tet", n3, "tile-pipe-" + shape, env={"NPB_TILE_PIPE": shape}, methods=("idw", "ls"))
