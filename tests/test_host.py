@@ -264,3 +264,69 @@ def test_pinned_pool_reuses_a_block_only_when_unreferenced(monkeypatch):
     assert len(allocs) == 3
     small = P.take("data", 10, np.float64)       # a block more than twice the request is never handed out:
     assert len(allocs) == 4 and small.base.size <= 2 * 10 + 64   # scipy would copy such a view
+
+
+def test_flag_row_is_restaged_by_slices_only_when_unchanged():
+    """Multi-GPU re-staging (interpolator._stage_inputs): with a resident flag row and a current partition a rank uploads
+    only the slice of its own nodes; the summed slice checksums decide whether that was enough.  Host logic only: the
+    device context is a stand-in that records what it is asked to do."""
+    calls = []
+
+    def checksum(flags):
+        return int(np.flatnonzero(np.asarray(flags) != 0).sum() * 2654435761 % (1 << 62))
+
+    class Ctx:
+        resident = None
+
+        def set_point_flags(self, flags):
+            calls.append(("full", flags.size))
+            Ctx.resident = checksum(flags)
+
+        def set_point_flags_slice(self, flags, first, count):
+            calls.append(("slice", first, count))
+            return checksum(flags)               # what the all-reduce of the ranks' slice checksums yields
+
+        def scalar(self, name):
+            assert name == "flags_checksum"
+            return Ctx.resident
+
+        def set_partition(self, bounds):
+            calls.append(("partition", tuple(int(b) for b in bounds)))
+
+    class Comm:
+        world, rank = 2, 1
+
+    class G:
+        n_points, n_elems, dim = 1000, 10, 3
+        esup_ptr = np.arange(0, 4 * 1001, 4)
+        boundary_points = np.zeros(1000, dtype=np.int64)
+
+    G.boundary_points[:100] = 1
+    I = _HostOnly()
+    I.grid, I.comm, I._ctx = G(), Comm(), Ctx()
+    I.pin_inputs, I._registered, I.last_timings = False, {}, {}
+    I._flag_mask, I._flag_version, I._partition_key, I._mesh_serial = None, 0, None, 1
+    I._pending_key = None
+    flags = np.zeros(1000)
+    flags[:50] = 1.0
+    I.variable_to_index = {"points": {"neumann_flag_u": 0}, "cells": {"u": 0}, "faces": {}}
+    I._rows = {"cells": [np.zeros(10)], "points": [flags]}
+    stage = lambda: I._stage_inputs("idw", "u", I.variable_to_index, I._rows["cells"], I._rows["points"])
+    stage()                                                     # first time: the whole row, then the node ranges
+    assert [c[0] for c in calls] == ["full", "partition"] and I.last_timings["h2d_input_bytes"] == 8000
+    bounds = calls[1][1]
+    calls.clear()
+    stage()                                                     # resident and keyed: nothing moves
+    assert calls == []
+    I.invalidate_inputs()
+    stage()                                                     # re-staged, unchanged: this rank's slice only
+    lo, hi = bounds[1], bounds[2]
+    assert calls == [("slice", lo, hi - lo)] and I.last_timings["h2d_input_bytes"] == 8 * (hi - lo)
+    calls.clear()
+    flags2 = flags.copy()
+    flags2[60:80] = 1.0                                         # changed outside this rank's slice too
+    I._rows["points"][0] = flags2
+    I._data_version += 1
+    stage()                                                     # the slice checksums do not add up: whole row, new cut
+    assert [c[0] for c in calls] == ["slice", "full", "partition"] and I.last_timings["h2d_input_bytes"] == 8000
+    assert I._flag_version == 2
